@@ -1,0 +1,57 @@
+// fluxb200 — operator-level C ABI (include/fluxb200.h).
+#include "fluxb200.h"
+#include "internal.h"
+#include "kernels.h"
+
+using namespace fb;
+
+extern "C" {
+
+const char* fluxb200_last_error(void) { return fb::last_error(); }
+int fluxb200_version(void) { return 100; }
+
+int fluxb200_linear(const void* a, int64_t lda, const void* w, int64_t ldw, const void* bias, void* out, int64_t ldo,
+                    int32_t M, int32_t N, int32_t K, int32_t bias_mode, int32_t act, const void* gate,
+                    int64_t gate_bstride, int32_t rows_per_batch, const void* res, float alpha,
+                    fluxb200_stream_t stream) {
+  GemmDesc d;
+  d.a = static_cast<const bf16*>(a), d.lda = lda;
+  d.w = static_cast<const bf16*>(w), d.ldb = ldw;
+  d.M = M, d.N = N, d.K = K;
+  d.out0 = static_cast<bf16*>(out), d.ld0 = ldo;
+  d.bias = static_cast<const bf16*>(bias);
+  d.bias_mode = bias ? bias_mode : BIAS_NONE;
+  d.act0 = act;
+  d.gate = static_cast<const bf16*>(gate), d.gate_bstride = gate_bstride, d.rows_per_batch = rows_per_batch;
+  d.res = static_cast<const bf16*>(res);
+  d.alpha = alpha;
+  return launch_gemm(&d, 1, static_cast<cudaStream_t>(stream));
+}
+
+int fluxb200_sdpa(const void* q, const void* k, const void* v, void* out, int32_t B, int32_t H, int32_t L,
+                  float scale, fluxb200_stream_t stream) {
+  AttnDesc d;
+  d.q = static_cast<const bf16*>(q), d.k = static_cast<const bf16*>(k), d.v = static_cast<const bf16*>(v);
+  d.B = B, d.H = H, d.L = L, d.scale = scale;
+  d.out_b = static_cast<bf16*>(out), d.ld_b = static_cast<int64_t>(H) * 128, d.l_split = 0;
+  return launch_attention(d, static_cast<cudaStream_t>(stream));
+}
+
+int fluxb200_layernorm_modulate(const void* x, const void* shift, const void* scale, int64_t mod_bstride, void* out,
+                                int32_t batch, int32_t rows_per_batch, int32_t dim, float eps,
+                                fluxb200_stream_t stream) {
+  return launch_ln_modulate(static_cast<const bf16*>(x), rows_per_batch, 0, rows_per_batch, batch,
+                            static_cast<const bf16*>(shift), static_cast<const bf16*>(scale), mod_bstride,
+                            static_cast<bf16*>(out), dim, eps, static_cast<cudaStream_t>(stream));
+}
+
+int fluxb200_qknorm_rope(const void* qkv, int64_t ld, int32_t batch, int32_t rows_per_batch, int32_t H, int32_t L,
+                         int32_t l_off, const void* wq, const void* wk, const void* pe_cos, const void* pe_sin,
+                         void* Q, void* K, void* V, float eps, fluxb200_stream_t stream) {
+  return launch_qknorm_rope(static_cast<const bf16*>(qkv), ld, rows_per_batch, batch, H, L, l_off,
+                            static_cast<const bf16*>(wq), static_cast<const bf16*>(wk),
+                            static_cast<const bf16*>(pe_cos), static_cast<const bf16*>(pe_sin), static_cast<bf16*>(Q),
+                            static_cast<bf16*>(K), static_cast<bf16*>(V), eps, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,99 @@
+// fluxb200 — error plumbing, device queries and TMA tensor-map encoding.
+#include <cudaTypedefs.h>
+
+#include <mutex>
+
+#include "internal.h"
+
+namespace fb {
+
+static thread_local std::string g_last_error;
+
+void set_error(const std::string& msg) { g_last_error = msg; }
+const char* last_error() { return g_last_error.c_str(); }
+int fail(const std::string& msg) {
+  g_last_error = msg;
+  return -1;
+}
+
+int num_sms() {
+  static int sms[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (sms[dev] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    sms[dev] = v;
+  }
+  return sms[dev];
+}
+
+// cuTensorMapEncodeTiled is a driver API; resolve it through the runtime so the library has no
+// link-time dependency on libcuda.so (it must load on a CPU-only build box).
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  });
+  return fn;
+}
+
+static int encode_nd(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                     const uint32_t* box) {
+  auto enc = get_encode();
+  if (!enc) return fail("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bdim[5];
+  cuuint32_t estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = 1;
+  }
+  for (int i = 0; i < rank - 1; ++i) gstr[i] = strides_bytes[i];
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    std::string s = "cuTensorMapEncodeTiled failed, CUresult=" + std::to_string(static_cast<int>(r)) + " rank=" +
+                    std::to_string(rank) + " dims=";
+    for (int i = 0; i < rank; ++i) s += std::to_string(dims[i]) + ",";
+    s += " strides=";
+    for (int i = 0; i < rank - 1; ++i) s += std::to_string(strides_bytes[i]) + ",";
+    s += " box=";
+    for (int i = 0; i < rank; ++i) s += std::to_string(box[i]) + ",";
+    return fail(s);
+  }
+  return 0;
+}
+
+int encode_tmap_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t outer_stride_bytes,
+                   uint32_t box_inner, uint32_t box_outer) {
+  uint64_t dims[2] = {inner, outer};
+  uint64_t str[1] = {outer_stride_bytes};
+  uint32_t box[2] = {box_inner, box_outer};
+  return encode_nd(out, base, 2, dims, str, box);
+}
+int encode_tmap_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
+                   uint64_t stride2_bytes, uint32_t b0, uint32_t b1, uint32_t b2) {
+  uint64_t dims[3] = {d0, d1, d2};
+  uint64_t str[2] = {stride1_bytes, stride2_bytes};
+  uint32_t box[3] = {b0, b1, b2};
+  return encode_nd(out, base, 3, dims, str, box);
+}
+int encode_tmap_4d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3,
+                   uint64_t stride1_bytes, uint64_t stride2_bytes, uint64_t stride3_bytes, uint32_t b0, uint32_t b1,
+                   uint32_t b2, uint32_t b3) {
+  uint64_t dims[4] = {d0, d1, d2, d3};
+  uint64_t str[3] = {stride1_bytes, stride2_bytes, stride3_bytes};
+  uint32_t box[4] = {b0, b1, b2, b3};
+  return encode_nd(out, base, 4, dims, str, box);
+}
+
+}  // namespace fb

@@ -1,0 +1,329 @@
+// fluxb200 — HBM-bound warp-reduction / elementwise kernels of the DiT step.
+// Each kernel fuses what the reference runs as a chain of separate bf16 tensor ops and keeps the
+// reference's rounding points (f32 op -> round-to-nearest-even bf16 after every tensor op).
+#include "internal.h"
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace fb {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  f[0] = bf_lo(u.x), f[1] = bf_hi(u.x), f[2] = bf_lo(u.y), f[3] = bf_hi(u.y);
+  f[4] = bf_lo(u.z), f[5] = bf_hi(u.z), f[6] = bf_lo(u.w), f[7] = bf_hi(u.w);
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 u;
+  u.x = pack_bf16(f[0], f[1]), u.y = pack_bf16(f[2], f[3]), u.z = pack_bf16(f[4], f[5]), u.w = pack_bf16(f[6], f[7]);
+  return u;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm(eps, no affine) + AdaLN modulate:  out = ((LN(x) -> bf16) * (1 + scale -> bf16) -> bf16) + shift -> bf16
+// reference: nn::LayerNorm fast path (nn/ops.rs:1021-1043 / reduce.cu:73-131) then ModulationOut::scale_shift
+// (models/flux/model.rs:217-221). One warp per row, the row stays in registers between the two passes.
+// ------------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(128) ln_modulate_kernel(const bf16* __restrict__ x, long long in_bstride_rows,
+                                                          int in_row_off, int rows_per_batch, int total_rows,
+                                                          const bf16* __restrict__ shift,
+                                                          const bf16* __restrict__ scale, long long mod_bstride,
+                                                          bf16* __restrict__ out, float eps) {
+  constexpr int VEC = D / 256;  // uint4 (8 bf16) per lane
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 4 + warp;
+  if (row >= total_rows) return;
+  const int b = row / rows_per_batch;
+  const int i = row - b * rows_per_batch;
+  const bf16* xr = x + (static_cast<long long>(b) * in_bstride_rows + in_row_off + i) * D;
+  float v[VEC][8];
+  float s = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) {
+    uint4 u = *reinterpret_cast<const uint4*>(xr + (k * 32 + lane) * 8);
+    unpack8(u, v[k]);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      s += v[k][e];
+      s2 += v[k][e] * v[k][e];
+    }
+  }
+  s = warp_sum(s);
+  s2 = warp_sum(s2);
+  const float mean = s / D;
+  const float var = s2 / D - mean * mean;
+  const float inv_std = 1.0f / sqrtf(var + eps);
+  const bf16* sh = shift + static_cast<long long>(b) * mod_bstride;
+  const bf16* sc = scale + static_cast<long long>(b) * mod_bstride;
+  bf16* orow = out + static_cast<long long>(row) * D;
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) {
+    const int c = (k * 32 + lane) * 8;
+    float fs[8], fc[8], o[8];
+    unpack8(*reinterpret_cast<const uint4*>(sh + c), fs);
+    unpack8(*reinterpret_cast<const uint4*>(sc + c), fc);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float n = rbf((v[k][e] - mean) * inv_std);
+      float m = rbf(n * rbf(fc[e] + 1.0f));
+      o[e] = rbf(m + fs[e]);
+    }
+    *reinterpret_cast<uint4*>(orow + c) = pack8(o);
+  }
+}
+
+int launch_ln_modulate(const bf16* x, long long in_bstride_rows, int in_row_off, int rows_per_batch, int batch,
+                       const bf16* shift, const bf16* scale, long long mod_bstride, bf16* out, int D, float eps,
+                       cudaStream_t stream) {
+  FB_REQUIRE(D == 3072, "ln_modulate: hidden size must be 3072 (HIDDEN_SIZE, model.rs:17)");
+  const int total = rows_per_batch * batch;
+  ln_modulate_kernel<3072><<<(total + 3) / 4, 128, 0, stream>>>(x, in_bstride_rows, in_row_off, rows_per_batch, total,
+                                                                shift, scale, mod_bstride, out, eps);
+  FB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// QK RMS-norm + RoPE + head-major relayout.
+//   in : qkv rows [rows, ld] with q | k | v at column offsets 0, D, 2D (bf16)
+//   out: Q, K, V [B, H, L, 128]; the stream's tokens land at sequence offset l_off (txt first, then img)
+// reference: SelfAttention::qkv (model.rs:399-427), RmsNorm slow path (nn/layer_norm.rs:136-153),
+//            apply_rope (model.rs:86-95): out0 = cos*x0 + (-sin)*x1, out1 = sin*x0 + cos*x1, every op rounded to bf16.
+// One warp per (token, head, q|k|v): 128 contiguous bf16 = 8 B per lane.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) qknorm_rope_kernel(const bf16* __restrict__ qkv, long long ld,
+                                                          int rows_per_batch, int H, int L, int l_off,
+                                                          const bf16* __restrict__ wq, const bf16* __restrict__ wk,
+                                                          const bf16* __restrict__ pe_cos,
+                                                          const bf16* __restrict__ pe_sin, bf16* __restrict__ Q,
+                                                          bf16* __restrict__ K, bf16* __restrict__ V, float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x;
+  const int b = row / rows_per_batch;
+  const int l = l_off + (row - b * rows_per_batch);
+  const int D = H * 128;
+  const bf16* base = qkv + static_cast<long long>(row) * ld;
+  for (int item = warp; item < 3 * H; item += 8) {
+    const int which = item / H;  // 0 q, 1 k, 2 v
+    const int h = item - which * H;
+    const uint2 u = *reinterpret_cast<const uint2*>(base + which * D + h * 128 + lane * 4);
+    bf16* dst = (which == 0 ? Q : (which == 1 ? K : V)) + ((static_cast<long long>(b) * H + h) * L + l) * 128 + lane * 4;
+    if (which == 2) {
+      *reinterpret_cast<uint2*>(dst) = u;
+      continue;
+    }
+    float x[4] = {bf_lo(u.x), bf_hi(u.x), bf_lo(u.y), bf_hi(u.y)};
+    float ss = x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3];
+    ss = warp_sum(ss);
+    const float denom = sqrtf(ss / 128.0f + eps);
+    const bf16* w = (which == 0 ? wq : wk) + lane * 4;
+    const uint2 wu = *reinterpret_cast<const uint2*>(w);
+    const float wf[4] = {bf_lo(wu.x), bf_hi(wu.x), bf_lo(wu.y), bf_hi(wu.y)};
+    float y[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) y[e] = rbf(rbf(x[e] / denom) * wf[e]);
+    // rope: pairs (2i, 2i+1), i = lane*2 + {0,1}
+    const uint32_t cu = *reinterpret_cast<const uint32_t*>(pe_cos + static_cast<long long>(l) * 64 + lane * 2);
+    const uint32_t su = *reinterpret_cast<const uint32_t*>(pe_sin + static_cast<long long>(l) * 64 + lane * 2);
+    const float c[2] = {bf_lo(cu), bf_hi(cu)};
+    const float s[2] = {bf_lo(su), bf_hi(su)};
+    float o[4];
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      const float x0 = y[2 * p], x1 = y[2 * p + 1];
+      o[2 * p] = rbf(rbf(c[p] * x0) + rbf(-s[p] * x1));
+      o[2 * p + 1] = rbf(rbf(s[p] * x0) + rbf(c[p] * x1));
+    }
+    uint2 ou;
+    ou.x = pack_bf16(o[0], o[1]);
+    ou.y = pack_bf16(o[2], o[3]);
+    *reinterpret_cast<uint2*>(dst) = ou;
+  }
+}
+
+int launch_qknorm_rope(const bf16* qkv, long long ld, int rows_per_batch, int batch, int H, int L, int l_off,
+                       const bf16* wq, const bf16* wk, const bf16* pe_cos, const bf16* pe_sin, bf16* Q, bf16* K,
+                       bf16* V, float eps, cudaStream_t stream) {
+  const int rows = rows_per_batch * batch;
+  qknorm_rope_kernel<<<rows, 256, 0, stream>>>(qkv, ld, rows_per_batch, H, L, l_off, wq, wk, pe_cos, pe_sin, Q, K, V,
+                                               eps);
+  FB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Batched skinny linears (M = batch <= 8): every AdaLN modulation projection of a step in ONE launch.
+//   out[b, n] = bf16( bf16( sum_k x[b,k] * W[n,k] ) + bias[n] )     (rank-2 path of UnquantLinear::forward,
+//   unquantized/mod.rs:67: matmul rounds to bf16, then a separate bf16 broadcast_add)
+// HBM-bound on the weights: one warp per output row streams W[n, :] once with 16-byte loads, x lives in smem.
+// ------------------------------------------------------------------------------------------------
+template <int BMAX>
+__global__ void __launch_bounds__(256) gemv_jobs_kernel(const GemvJob* __restrict__ jobs, int njobs, int total_rows,
+                                                        const bf16* __restrict__ x, long long x_ld, int B, int K) {
+  extern __shared__ uint8_t smem_raw[];
+  bf16* xs = reinterpret_cast<bf16*>(smem_raw);  // [B][K]
+  for (int i = threadIdx.x; i < B * (K / 8); i += blockDim.x) {
+    const int b = i / (K / 8), c = i - b * (K / 8);
+    reinterpret_cast<uint4*>(xs)[i] = *reinterpret_cast<const uint4*>(x + b * x_ld + c * 8);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int ROWS_PER_WARP = 4;
+  const int row0 = (blockIdx.x * 8 + warp) * ROWS_PER_WARP;
+  for (int rr = 0; rr < ROWS_PER_WARP; ++rr) {
+    const int grow = row0 + rr;
+    if (grow >= total_rows) return;
+    int lo = 0, hi = njobs - 1;  // last job with row_begin <= grow
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (jobs[mid].row_begin <= grow) lo = mid; else hi = mid - 1;
+    }
+    const GemvJob job = jobs[lo];
+    const int n = grow - job.row_begin;
+    const bf16* wr = job.w + static_cast<long long>(n) * K;
+    float acc[BMAX];
+#pragma unroll
+    for (int b = 0; b < BMAX; ++b) acc[b] = 0.f;
+    for (int c = lane; c < K / 8; c += 32) {
+      float wf[8];
+      unpack8(*reinterpret_cast<const uint4*>(wr + c * 8), wf);
+#pragma unroll
+      for (int b = 0; b < BMAX; ++b) {
+        if (b < B) {
+          float xf[8];
+          unpack8(reinterpret_cast<const uint4*>(xs + b * K)[c], xf);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[b] = fmaf(wf[e], xf[e], acc[b]);
+        }
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < BMAX; ++b) acc[b] = warp_sum(acc[b]);
+    if (lane == 0) {
+      const float bias = job.bias ? __bfloat162float(job.bias[n]) : 0.f;
+#pragma unroll
+      for (int b = 0; b < BMAX; ++b) {
+        if (b < B) {
+          float v = rbf(acc[b]);
+          if (job.bias) v = rbf(v + bias);
+          job.out[b * job.out_ld + n] = __float2bfloat16_rn(v);
+        }
+      }
+    }
+  }
+}
+
+int launch_gemv_jobs(const GemvJob* jobs_dev, int njobs, int total_rows, const bf16* x, long long x_ld, int B, int K,
+                     cudaStream_t stream) {
+  FB_REQUIRE(B >= 1 && B <= 8, "gemv_jobs: batch must be in 1..8");
+  FB_REQUIRE(K % 8 == 0, "gemv_jobs: K must be a multiple of 8");
+  const size_t smem = static_cast<size_t>(B) * K * 2;
+  FB_REQUIRE(smem <= 96 * 1024, "gemv_jobs: batch*K too large for shared memory");
+  const int grid = (total_rows + 31) / 32;
+  if (B <= 2) {
+    static bool set2 = false;
+    if (!set2) {
+      FB_CHECK_CUDA(cudaFuncSetAttribute(gemv_jobs_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      set2 = true;
+    }
+    gemv_jobs_kernel<2><<<grid, 256, smem, stream>>>(jobs_dev, njobs, total_rows, x, x_ld, B, K);
+  } else {
+    static bool set8 = false;
+    if (!set8) {
+      FB_CHECK_CUDA(cudaFuncSetAttribute(gemv_jobs_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      set8 = true;
+    }
+    gemv_jobs_kernel<8><<<grid, 256, smem, stream>>>(jobs_dev, njobs, total_rows, x, x_ld, B, K);
+  }
+  FB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// small per-step kernels
+// ------------------------------------------------------------------------------------------------
+// SiLU in bf16 steps: v / (1 + exp(-v))  (core/op.rs:699-706)
+__global__ void silu_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, long long n) {
+  long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const float v = __bfloat162float(x[i]);
+  const float e = rbf(expf(-v));
+  const float d = rbf(1.0f + e);
+  y[i] = __float2bfloat16_rn(v / d);
+}
+int launch_silu(const bf16* x, bf16* y, long long n, cudaStream_t stream) {
+  silu_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(x, y, n);
+  FB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// timestep_embedding (model.rs:104-122): t*1000; freqs = exp(k * (-ln(1e4)/half)); [cos | sin] (f32) -> bf16
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, bf16* __restrict__ out, int B, int dim) {
+  const int half = dim / 2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * half) return;
+  const int b = i / half, k = i - b * half;
+  const float tt = t[b] * 1000.0f;
+  const float coef = static_cast<float>(-9.210340371976184 / static_cast<double>(half));  // -ln(10000)/half
+  const float freq = expf(static_cast<float>(k) * coef);
+  const float arg = tt * freq;
+  out[b * dim + k] = __float2bfloat16_rn(cosf(arg));
+  out[b * dim + half + k] = __float2bfloat16_rn(sinf(arg));
+}
+int launch_timestep_embedding(const float* t, bf16* out, int B, int dim, cudaStream_t stream) {
+  const int n = B * dim / 2;
+  timestep_embedding_kernel<<<(n + 127) / 128, 128, 0, stream>>>(t, out, B, dim);
+  FB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// vec_ = (a [+ g]) + y, each add rounded to bf16 (model.rs:813-820)
+__global__ void vec_combine_kernel(const bf16* __restrict__ a, const bf16* __restrict__ g, const bf16* __restrict__ y,
+                                   bf16* __restrict__ out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v = __bfloat162float(a[i]);
+  if (g) v = rbf(v + __bfloat162float(g[i]));
+  v = rbf(v + __bfloat162float(y[i]));
+  out[i] = __float2bfloat16_rn(v);
+}
+int launch_vec_combine(const bf16* a, const bf16* g, const bf16* y, bf16* out, int n, cudaStream_t stream) {
+  vec_combine_kernel<<<(n + 255) / 256, 256, 0, stream>>>(a, g, y, out, n);
+  FB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Euler update (pipelines/sampling.rs:43): img = img + pred * dt ; dt rounded to bf16 by the affine op, two roundings
+__global__ void euler_kernel(bf16* __restrict__ img, const bf16* __restrict__ pred, float dt_bf16, long long n) {
+  long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const float p = rbf(__bfloat162float(pred[i]) * dt_bf16);
+  img[i] = __float2bfloat16_rn(__bfloat162float(img[i]) + p);
+}
+int launch_euler(bf16* img, const bf16* pred, float dt, long long n, cudaStream_t stream) {
+  const float dtb = __bfloat162float(__float2bfloat16_rn(dt));
+  euler_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(img, pred, dtb, n);
+  FB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// out = x * mul + add with bf16 scalars and two roundings (Tensor::affine on bf16, cuda_kernels/affine.cu:33)
+__global__ void affine_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, float mul_b, float add_b, long long n) {
+  long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  y[i] = __float2bfloat16_rn(rbf(__bfloat162float(x[i]) * mul_b) + add_b);
+}
+int launch_affine(const bf16* x, bf16* y, float mul, float add, long long n, cudaStream_t stream) {
+  const float mb = __bfloat162float(__float2bfloat16_rn(mul));
+  const float ab = __bfloat162float(__float2bfloat16_rn(add));
+  affine_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(x, y, mb, ab, n);
+  FB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace fb

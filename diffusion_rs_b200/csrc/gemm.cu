@@ -1,0 +1,405 @@
+// fluxb200 — persistent, warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   out[M,N] = epilogue( A[M,K] . W[N,K]^T )      A, W bf16 (K contiguous), fp32 accumulation in TMEM.
+//
+// Replaces, on the hot path, every cuBLAS/cuBLASLt call the reference makes for a Linear
+// (diffusion_rs_backend/src/unquantized/mod.rs:34-77, cublaslt/matmul.rs:502-586) and, in conv mode,
+// the im2col + GEMM + NHWC->NCHW copy of diffusion_rs_common/src/core/cuda_backend/mod.rs:1545-1599.
+//
+// Structure (one CTA per SM, 192 threads):
+//   warp 0      TMA producer   : 4-stage ring of {A 128x64, W 256x64} bf16 tiles, 128B swizzle
+//   warp 1      MMA issuer     : tcgen05.mma cta_group::1 kind::f16, M=128 N=256 K=16, accumulators in TMEM
+//   warps 2..5  epilogue       : tcgen05.ld -> fused bias / GELU / alpha / gate*x+residual -> bf16 global stores
+// TMEM holds two 128x256 fp32 accumulators so the epilogue of tile i overlaps the mainloop of tile i+1.
+// A launch may carry up to 4 problems (grouped GEMM) so the 512-token text stream shares a wave with the
+// 4096-token image stream instead of leaving 2/3 of the SMs idle.
+#include <vector>
+
+#include "internal.h"
+#include "ptx.cuh"
+
+namespace fb {
+
+static constexpr int BLOCK_M = 128;
+static constexpr int BLOCK_N = 256;
+static constexpr int BLOCK_K = 64;
+static constexpr int STAGES = 4;
+static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
+static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;  // 32 KB
+static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+static constexpr int GEMM_THREADS = 192;
+static constexpr int MAX_PROBLEMS = 4;
+static constexpr int GROUP_M = 8;
+static constexpr int CONV_TH = 8, CONV_TW = 16;  // 8x16 output pixels = one 128-row M tile
+static constexpr size_t GEMM_SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+struct alignas(64) GemmProblemDev {
+  CUtensorMap tmap_a;
+  CUtensorMap tmap_b;
+  int M, N, K, num_kb;
+  int tiles_m, tiles_n, tile_begin, tile_end;
+  int conv, cH, cW, cC, c_chunks, ksize, tiles_h, tiles_w;
+  bf16* out0;
+  bf16* out1;
+  long long ld0, ld1;
+  int n_split, col_off1, act0, act1;
+  const bf16* bias;
+  const bf16* gate;
+  const bf16* res;
+  long long gate_bstride;
+  int rows_per_batch, bias_mode, has_alpha;
+  float alpha;
+};
+
+struct GemmParams {
+  GemmProblemDev p[MAX_PROBLEMS];
+  int count;
+  int total_tiles;
+};
+
+// tanh-GELU with the reference's bf16 op-by-op rounding (diffusion_rs_common/src/core/op.rs:539-578):
+//   0.5*v*(1 + tanh(c*v*(1 + 0.044715*v*v)))   evaluated left to right, every product/sum rounded to bf16.
+__device__ __forceinline__ float gelu_bf16_steps(float v) {
+  const float kHalf = 0.5f;
+  const float kC = __bfloat162float(__float2bfloat16_rn(0.79788456080286535587989211986876373f));
+  const float kK = __bfloat162float(__float2bfloat16_rn(0.044715f));
+  float a = rbf(kHalf * v);
+  float p = rbf(1.0f + rbf(rbf(kK * v) * v));
+  float q = rbf(rbf(kC * v) * p);
+  float t = rbf(tanhf(q));
+  float s = rbf(1.0f + t);
+  return rbf(a * s);
+}
+
+struct TileCoord {
+  int prob, m_t, n_t;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const GemmParams& P, int t) {
+  int pi = 0;
+#pragma unroll
+  for (int i = 1; i < MAX_PROBLEMS; ++i)
+    if (i < P.count && t >= P.p[i].tile_begin) pi = i;
+  const GemmProblemDev& p = P.p[pi];
+  int lt = t - p.tile_begin;
+  int group_size = GROUP_M * p.tiles_n;
+  int g = lt / group_size;
+  int first_m = g * GROUP_M;
+  int gm = min(p.tiles_m - first_m, GROUP_M);
+  int in_g = lt - g * group_size;
+  TileCoord c;
+  c.prob = pi;
+  c.m_t = first_m + in_g % gm;
+  c.n_t = in_g / gm;
+  return c;
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  // 128B swizzle needs 1024-byte aligned tiles
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;  // [2]
+  uint64_t* tmem_empty = tmem_full + 2;      // [2]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < P.count; ++i) {
+      tma_prefetch_desc(&P.p[i].tmap_a);
+      tma_prefetch_desc(&P.p[i].tmap_b);
+    }
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 4);  // one arrival per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_base_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
+        TileCoord tc = decode_tile(P, t);
+        const GemmProblemDev& p = P.p[tc.prob];
+        int cn = 0, ch0 = 0, cw0 = 0;
+        if (p.conv) {
+          int per_img = p.tiles_h * p.tiles_w;
+          cn = tc.m_t / per_img;
+          int rem = tc.m_t - cn * per_img;
+          ch0 = (rem / p.tiles_w) * CONV_TH;
+          cw0 = (rem % p.tiles_w) * CONV_TW;
+        }
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          uint8_t* sb = sa + A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+          if (p.conv) {
+            int tap = kb / p.c_chunks;
+            int cc = kb - tap * p.c_chunks;
+            int kh = tap / p.ksize, kw = tap - kh * p.ksize;
+            int pad = p.ksize >> 1;
+            tma_load_4d(sa, &p.tmap_a, &full_bar[stage], cc * BLOCK_K, cw0 + kw - pad, ch0 + kh - pad, cn);
+            tma_load_2d(sb, &p.tmap_b, &full_bar[stage], tap * p.cC + cc * BLOCK_K, tc.n_t * BLOCK_N);
+          } else {
+            tma_load_2d(sa, &p.tmap_a, &full_bar[stage], kb * BLOCK_K, tc.m_t * BLOCK_M);
+            tma_load_2d(sb, &p.tmap_b, &full_bar[stage], kb * BLOCK_K, tc.n_t * BLOCK_N);
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (single thread) =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
+        TileCoord tc = decode_tile(P, t);
+        const GemmProblemDev& p = P.p[tc.prob];
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint64_t da = umma_smem_desc_sw128(sa, 16, 1024);
+          const uint64_t db = umma_smem_desc_sw128(sa + A_BYTES, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k) {
+            // advance 16 bf16 = 32 B along K inside the 128B swizzle atom: +2 in the (addr >> 4) field
+            umma_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          }
+          tc_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        tc_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ================= epilogue warps =================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
+      TileCoord tc = decode_tile(P, t);
+      const GemmProblemDev& p = P.p[tc.prob];
+      const int r = q * 32 + lane;  // row inside the tile == TMEM lane
+      long long grow;
+      bool valid;
+      if (p.conv) {
+        int per_img = p.tiles_h * p.tiles_w;
+        int cn = tc.m_t / per_img;
+        int rem = tc.m_t - cn * per_img;
+        int h = (rem / p.tiles_w) * CONV_TH + r / CONV_TW;
+        int w = (rem % p.tiles_w) * CONV_TW + r % CONV_TW;
+        valid = (h < p.cH) && (w < p.cW);
+        grow = (static_cast<long long>(cn) * p.cH + h) * p.cW + w;
+      } else {
+        grow = static_cast<long long>(tc.m_t) * BLOCK_M + r;
+        valid = grow < p.M;
+      }
+      const long long gate_off =
+          (p.gate != nullptr) ? (p.rows_per_batch > 0 ? grow / p.rows_per_batch : 0) * p.gate_bstride : 0;
+
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
+
+#pragma unroll 1
+      for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
+        const int n0 = tc.n_t * BLOCK_N + chunk * 32;
+        if (n0 >= p.N) break;  // warp-uniform
+        uint32_t acc_r[32];
+        tmem_ld32(t_row + chunk * 32, acc_r);
+        tc_wait_ld();
+        if (!valid) continue;
+        const bool seg1 = (p.n_split > 0) && (n0 >= p.n_split);
+        bf16* outp = seg1 ? p.out1 + grow * p.ld1 + (n0 - p.n_split + p.col_off1) : p.out0 + grow * p.ld0 + n0;
+        const int act = seg1 ? p.act1 : p.act0;
+        const bf16* resp = (p.res != nullptr && !seg1) ? p.res + grow * p.ld0 + n0 : nullptr;
+        const bf16* gatep = (p.gate != nullptr && !seg1) ? p.gate + gate_off + n0 : nullptr;
+        const bf16* biasp = (p.bias_mode != BIAS_NONE) ? p.bias + n0 : nullptr;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int nj = n0 + j * 8;
+          if (nj >= p.N) break;
+          const bool full8 = (nj + 8 <= p.N);
+          float bv[8], gv[8], rv[8];
+          if (full8) {
+            if (biasp) {
+              uint4 u = *reinterpret_cast<const uint4*>(biasp + j * 8);
+              bv[0] = bf_lo(u.x), bv[1] = bf_hi(u.x), bv[2] = bf_lo(u.y), bv[3] = bf_hi(u.y);
+              bv[4] = bf_lo(u.z), bv[5] = bf_hi(u.z), bv[6] = bf_lo(u.w), bv[7] = bf_hi(u.w);
+            }
+            if (gatep) {
+              uint4 u = *reinterpret_cast<const uint4*>(gatep + j * 8);
+              gv[0] = bf_lo(u.x), gv[1] = bf_hi(u.x), gv[2] = bf_lo(u.y), gv[3] = bf_hi(u.y);
+              gv[4] = bf_lo(u.z), gv[5] = bf_hi(u.z), gv[6] = bf_lo(u.w), gv[7] = bf_hi(u.w);
+            }
+            if (resp) {
+              uint4 u = *reinterpret_cast<const uint4*>(resp + j * 8);
+              rv[0] = bf_lo(u.x), rv[1] = bf_hi(u.x), rv[2] = bf_lo(u.y), rv[3] = bf_hi(u.y);
+              rv[4] = bf_lo(u.z), rv[5] = bf_hi(u.z), rv[6] = bf_lo(u.w), rv[7] = bf_hi(u.w);
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const bool in = nj + e < p.N;
+              bv[e] = (biasp && in) ? __bfloat162float(biasp[j * 8 + e]) : 0.f;
+              gv[e] = (gatep && in) ? __bfloat162float(gatep[j * 8 + e]) : 0.f;
+              rv[e] = (resp && in) ? __bfloat162float(resp[j * 8 + e]) : 0.f;
+            }
+          }
+          float o[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float v = __uint_as_float(acc_r[j * 8 + e]);
+            if (p.bias_mode == BIAS_FUSED) {
+              v = rbf(v + bv[e]);  // bias enters the fp32 accumulator (cuBLASLt C operand, beta = 1)
+            } else {
+              v = rbf(v);
+              if (p.bias_mode == BIAS_AFTER_ROUND) v = rbf(v + bv[e]);  // separate bf16 broadcast_add
+            }
+            if (p.has_alpha) v = rbf(v * p.alpha);
+            if (act == ACT_GELU) v = gelu_bf16_steps(v);
+            if (gatep) v = rbf(gv[e] * v);
+            if (resp) v = rbf(rv[e] + v);
+            o[e] = v;
+          }
+          if (full8) {
+            uint4 u;
+            u.x = pack_bf16(o[0], o[1]);
+            u.y = pack_bf16(o[2], o[3]);
+            u.z = pack_bf16(o[4], o[5]);
+            u.w = pack_bf16(o[6], o[7]);
+            *reinterpret_cast<uint4*>(outp + j * 8) = u;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              if (nj + e < p.N) outp[j * 8 + e] = __float2bfloat16_rn(o[e]);
+          }
+        }
+      }
+      // release the accumulator back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+int launch_gemm(const GemmDesc* descs, int count, cudaStream_t stream) {
+  FB_REQUIRE(count >= 1 && count <= MAX_PROBLEMS, "launch_gemm: 1..4 problems per launch");
+  static bool attr_set = false;
+  if (!attr_set) {
+    FB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(GEMM_SMEM)));
+    attr_set = true;
+  }
+  GemmParams P;
+  memset(&P, 0, sizeof(P));
+  P.count = count;
+  int tile = 0;
+  for (int i = 0; i < count; ++i) {
+    const GemmDesc& d = descs[i];
+    GemmProblemDev& p = P.p[i];
+    FB_REQUIRE(d.a && d.w && d.out0, "launch_gemm: null operand");
+    FB_REQUIRE(d.M > 0 && d.N > 0 && d.K > 0, "launch_gemm: empty problem");
+    FB_REQUIRE((reinterpret_cast<uintptr_t>(d.a) & 15) == 0 && (reinterpret_cast<uintptr_t>(d.w) & 15) == 0,
+               "launch_gemm: operands must be 16-byte aligned (TMA)");
+    FB_REQUIRE((reinterpret_cast<uintptr_t>(d.out0) & 15) == 0 || (d.N % 8) != 0,
+               "launch_gemm: output must be 16-byte aligned");
+    FB_REQUIRE(d.n_split % BLOCK_N == 0, "launch_gemm: n_split must be a multiple of 256");
+    if (d.n_split > 0) FB_REQUIRE(d.out1 != nullptr, "launch_gemm: n_split without out1");
+    if (d.bias_mode != BIAS_NONE) FB_REQUIRE(d.bias != nullptr, "launch_gemm: bias_mode without bias");
+    p.M = d.M, p.N = d.N, p.K = d.K;
+    p.conv = d.conv;
+    if (d.conv) {
+      FB_REQUIRE(d.ksize == 1 || d.ksize == 3, "launch_gemm: conv ksize must be 1 or 3");
+      FB_REQUIRE(d.cC % 8 == 0, "launch_gemm: conv channels must be a multiple of 8");
+      FB_REQUIRE(d.K == d.ksize * d.ksize * d.cC, "launch_gemm: conv K != taps*C");
+      FB_REQUIRE(static_cast<long long>(d.cN) * d.cH * d.cW == d.M, "launch_gemm: conv M != N*H*W");
+      p.cH = d.cH, p.cW = d.cW, p.cC = d.cC, p.ksize = d.ksize;
+      p.c_chunks = (d.cC + BLOCK_K - 1) / BLOCK_K;
+      p.tiles_h = (d.cH + CONV_TH - 1) / CONV_TH;
+      p.tiles_w = (d.cW + CONV_TW - 1) / CONV_TW;
+      p.tiles_m = d.cN * p.tiles_h * p.tiles_w;
+      p.num_kb = d.ksize * d.ksize * p.c_chunks;
+      int rc = encode_tmap_4d(&p.tmap_a, d.a, d.cC, d.cW, d.cH, d.cN, static_cast<uint64_t>(d.cC) * 2,
+                              static_cast<uint64_t>(d.cW) * d.cC * 2, static_cast<uint64_t>(d.cH) * d.cW * d.cC * 2,
+                              BLOCK_K, CONV_TW, CONV_TH, 1);
+      if (rc) return rc;
+    } else {
+      FB_REQUIRE(d.K % 8 == 0 && d.lda % 8 == 0, "launch_gemm: K and lda must be multiples of 8");
+      p.tiles_m = (d.M + BLOCK_M - 1) / BLOCK_M;
+      p.num_kb = (d.K + BLOCK_K - 1) / BLOCK_K;
+      int rc = encode_tmap_2d(&p.tmap_a, d.a, d.K, d.M, static_cast<uint64_t>(d.lda) * 2, BLOCK_K, BLOCK_M);
+      if (rc) return rc;
+    }
+    FB_REQUIRE(d.ldb % 8 == 0, "launch_gemm: ldb must be a multiple of 8");
+    {
+      int rc = encode_tmap_2d(&p.tmap_b, d.w, d.K, d.N, static_cast<uint64_t>(d.ldb) * 2, BLOCK_K, BLOCK_N);
+      if (rc) return rc;
+    }
+    p.tiles_n = (d.N + BLOCK_N - 1) / BLOCK_N;
+    p.tile_begin = tile;
+    tile += p.tiles_m * p.tiles_n;
+    p.tile_end = tile;
+    p.out0 = d.out0, p.ld0 = d.ld0, p.out1 = d.out1, p.ld1 = d.ld1;
+    p.n_split = d.n_split, p.col_off1 = d.col_off1, p.act0 = d.act0, p.act1 = d.act1;
+    p.bias = d.bias, p.bias_mode = d.bias_mode;
+    p.gate = d.gate, p.gate_bstride = d.gate_bstride, p.rows_per_batch = d.rows_per_batch, p.res = d.res;
+    p.alpha = d.alpha, p.has_alpha = (d.alpha != 1.0f);
+  }
+  P.total_tiles = tile;
+  int grid = std::min(tile, num_sms());
+  gemm_tcgen05_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(P);
+  FB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace fb

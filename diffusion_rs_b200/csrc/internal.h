@@ -1,0 +1,92 @@
+// fluxb200 internal interfaces between translation units (not part of the C ABI).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+typedef __nv_bfloat16 bf16;
+
+namespace fb {
+
+// ---- error plumbing (thread-local last error, returned through the C ABI) ----
+void set_error(const std::string& msg);
+const char* last_error();
+int fail(const std::string& msg);  // sets error, returns -1
+
+#define FB_CHECK_CUDA(expr)                                                                          \
+  do {                                                                                               \
+    cudaError_t _e = (expr);                                                                         \
+    if (_e != cudaSuccess) {                                                                         \
+      return ::fb::fail(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " at " __FILE__ + ":" + \
+                        std::to_string(__LINE__));                                                   \
+    }                                                                                                \
+  } while (0)
+
+#define FB_REQUIRE(cond, msg)                        \
+  do {                                               \
+    if (!(cond)) return ::fb::fail(std::string(msg)); \
+  } while (0)
+
+// ---- tensor-map encoding (driver entry point resolved at run time; no link-time libcuda dependency) ----
+int encode_tmap_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t outer_stride_bytes,
+                   uint32_t box_inner, uint32_t box_outer);
+int encode_tmap_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
+                   uint64_t stride2_bytes, uint32_t b0, uint32_t b1, uint32_t b2);
+int encode_tmap_4d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3,
+                   uint64_t stride1_bytes, uint64_t stride2_bytes, uint64_t stride3_bytes, uint32_t b0, uint32_t b1,
+                   uint32_t b2, uint32_t b3);
+
+int num_sms();
+
+// ---- tcgen05 GEMM  out[M,N] = epilogue(A[M,K] . W[N,K]^T) ----
+enum { ACT_NONE = 0, ACT_GELU = 1 };
+enum { BIAS_NONE = 0, BIAS_FUSED = 1, BIAS_AFTER_ROUND = 2 };
+
+struct GemmDesc {
+  // operands (bf16, row-major, K contiguous). lda/ldb in elements.
+  const bf16* a = nullptr;
+  int64_t lda = 0;
+  const bf16* w = nullptr;
+  int64_t ldb = 0;
+  int M = 0, N = 0, K = 0;
+  // implicit-GEMM 3x3/1x1 convolution: A is an NHWC image [cN, cH, cW, cC]; M = cN*cH*cW output pixels,
+  // K = taps*cC with W laid out [N, taps, cC]; ksize in {1,3}, padding = ksize/2, stride 1.
+  int conv = 0, cN = 0, cH = 0, cW = 0, cC = 0, ksize = 0;
+  // outputs: columns [0, n_split) -> out0 (ld0); columns [n_split, N) -> out1 at column (n - n_split + col_off1)
+  bf16* out0 = nullptr;
+  int64_t ld0 = 0;
+  bf16* out1 = nullptr;
+  int64_t ld1 = 0;
+  int n_split = 0;  // 0 => everything to out0
+  int col_off1 = 0;
+  int act0 = ACT_NONE, act1 = ACT_NONE;
+  const bf16* bias = nullptr;
+  int bias_mode = BIAS_NONE;
+  float alpha = 1.f;  // if != 1: out = bf16(bf16(acc) * alpha) (alpha must be bf16-representable)
+  // out = res + gate * val (per-batch gate vector), applied when gate != nullptr
+  const bf16* gate = nullptr;
+  int64_t gate_bstride = 0;
+  int rows_per_batch = 0;
+  const bf16* res = nullptr;  // same ld as out0; may alias out0; may be used without gate (plain residual add)
+};
+// One persistent launch over up to 4 problems (grouped): img + txt streams share the machine.
+int launch_gemm(const GemmDesc* descs, int count, cudaStream_t stream);
+
+// ---- tcgen05 flash attention: q,k,v [B,H,L,128] bf16 -> out rows [B, L, H*128] split at L_split ----
+struct AttnDesc {
+  const bf16 *q = nullptr, *k = nullptr, *v = nullptr;
+  int B = 0, H = 0, L = 0;
+  float scale = 0.f;
+  // token l < l_split goes to out_a[(b*l_split + l)*ld_a + h*128 ...], else out_b[(b*(L-l_split) + l-l_split)*ld_b ...]
+  bf16* out_a = nullptr;
+  int64_t ld_a = 0;
+  bf16* out_b = nullptr;
+  int64_t ld_b = 0;
+  int l_split = 0;
+};
+int launch_attention(const AttnDesc& d, cudaStream_t stream);
+
+}  // namespace fb

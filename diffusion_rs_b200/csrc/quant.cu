@@ -1,0 +1,240 @@
+// fluxb200 — quantised-weight expansion: bitsandbytes NF4 / FP4 / blockwise-int8 / LLM.int8 and GGUF Q4_K.
+//
+// Exports the 12 `extern "C"` symbols of the reference's own FFI with identical signatures
+// (diffusion_rs_backend/src/bitsandbytes/ffi.rs:5-114; C side kernels/bitsandbytes/dequant.cu:172-232) so the Rust
+// `BnbLinear` links against this library unchanged, plus bf16 launchers used by the fused linear path.
+// Semantics are the reference CUDA kernel's (ground truth per SURVEY N4):
+//   4-bit : out[2j] = T(LUT[q>>4] * absmax[j / (blocksize/2)]),  out[2j+1] = T(LUT[q&15] * absmax[...])
+//   8-bit : out[i]  = T(code[q[i]] * absmax[i / blocksize])
+//   int8  : out[i]  = T(float(w[i]) * scb[i / col] / 127)
+// HBM-bound: one thread expands 16 packed bytes (32 weights) with 128-bit loads/stores.
+#include <cuda_fp16.h>
+
+#include "internal.h"
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace fb {
+
+__constant__ float kNF4[16] = {-1.0f,
+                               -0.6961928009986877f,
+                               -0.5250730514526367f,
+                               -0.39491748809814453f,
+                               -0.28444138169288635f,
+                               -0.18477343022823334f,
+                               -0.09105003625154495f,
+                               0.0f,
+                               0.07958029955625534f,
+                               0.16093020141124725f,
+                               0.24611230194568634f,
+                               0.33791524171829224f,
+                               0.44070982933044434f,
+                               0.5626170039176941f,
+                               0.7229568362236023f,
+                               1.0f};
+// sign-magnitude tree of dDequantizeFP4Tree (dequant.cu:12-37); bit 3 is the sign
+__constant__ float kFP4[16] = {0.0f,  5.208333333e-03f,  0.66666667f,  1.0f,  0.33333333f,  0.5f,  0.16666667f,  0.25f,
+                               -0.0f, -5.208333333e-03f, -0.66666667f, -1.0f, -0.33333333f, -0.5f, -0.16666667f, -0.25f};
+
+template <typename T>
+__device__ __forceinline__ T cvt_out(float v);
+template <>
+__device__ __forceinline__ float cvt_out<float>(float v) {
+  return v;
+}
+template <>
+__device__ __forceinline__ __half cvt_out<__half>(float v) {
+  return __float2half_rn(v);
+}
+template <>
+__device__ __forceinline__ bf16 cvt_out<bf16>(float v) {
+  return __float2bfloat16_rn(v);
+}
+
+// DATA_TYPE: 1 = FP4, 2 = NF4.  `half_block` = blocksize/2 = packed bytes per absmax entry.
+template <typename T, int DATA_TYPE>
+__global__ void __launch_bounds__(256) dequant_4bit_kernel(const uint8_t* __restrict__ A,
+                                                           const float* __restrict__ absmax, T* __restrict__ out,
+                                                           int half_block, long long n) {
+  const long long nbytes = (n + 1) / 2;
+  const long long byte0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * 16;
+  if (byte0 >= nbytes) return;
+  const float* lut = (DATA_TYPE == 2) ? kNF4 : kFP4;
+  const bool fast = (byte0 + 16 <= nbytes) && (2 * (byte0 + 16) <= n) && (half_block % 16 == 0) &&
+                    ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  if (fast) {
+    const uint4 pk = *reinterpret_cast<const uint4*>(A + byte0);
+    const float am = __ldg(&absmax[byte0 / half_block]);
+    const uint32_t words[4] = {pk.x, pk.y, pk.z, pk.w};
+    T vals[32];
+#pragma unroll
+    for (int w = 0; w < 4; ++w)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const uint32_t q = (words[w] >> (8 * b)) & 0xffu;
+        vals[(w * 4 + b) * 2] = cvt_out<T>(lut[q >> 4] * am);
+        vals[(w * 4 + b) * 2 + 1] = cvt_out<T>(lut[q & 15] * am);
+      }
+    constexpr int VEC = 16 / sizeof(T);  // elements per 16-byte store
+    T* o = out + byte0 * 2;
+#pragma unroll
+    for (int i = 0; i < 32 / VEC; ++i) reinterpret_cast<uint4*>(o)[i] = reinterpret_cast<const uint4*>(vals)[i];
+  } else {
+    for (int j = 0; j < 16; ++j) {
+      const long long bi = byte0 + j;
+      if (bi >= nbytes) break;
+      const uint32_t q = A[bi];
+      const float am = absmax[bi / half_block];
+      if (2 * bi < n) out[2 * bi] = cvt_out<T>(lut[q >> 4] * am);
+      if (2 * bi + 1 < n) out[2 * bi + 1] = cvt_out<T>(lut[q & 15] * am);
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) dequant_8bit_blockwise_kernel(const float* __restrict__ code,
+                                                                     const uint8_t* __restrict__ A,
+                                                                     const float* __restrict__ absmax,
+                                                                     T* __restrict__ out, int blocksize, long long n) {
+  __shared__ float scode[256];
+  scode[threadIdx.x] = code[threadIdx.x];
+  __syncthreads();
+  const long long i0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * 16;
+  for (int j = 0; j < 16; ++j) {
+    const long long i = i0 + j;
+    if (i >= n) return;
+    out[i] = cvt_out<T>(scode[A[i]] * absmax[i / blocksize]);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) dequant_int8_rowwise_kernel(const int8_t* __restrict__ w,
+                                                                   const float* __restrict__ scb, T* __restrict__ out,
+                                                                   int col, long long n) {
+  const long long i0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * 16;
+  for (int j = 0; j < 16; ++j) {
+    const long long i = i0 + j;
+    if (i >= n) return;
+    out[i] = cvt_out<T>((static_cast<float>(w[i]) * scb[i / col]) / 127.f);
+  }
+}
+
+template <typename T, int DATA_TYPE>
+static void dequant_blockwise(const float* code, const uint8_t* A, const float* absmax, T* out, int blocksize, int n,
+                              cudaStream_t stream) {
+  if (n <= 0) return;
+  if (DATA_TYPE > 0) {
+    const long long nbytes = (static_cast<long long>(n) + 1) / 2;
+    const unsigned grid = static_cast<unsigned>((nbytes + 16 * 256 - 1) / (16 * 256));
+    dequant_4bit_kernel<T, DATA_TYPE><<<grid, 256, 0, stream>>>(A, absmax, out, blocksize / 2, n);
+  } else {
+    const unsigned grid = static_cast<unsigned>((static_cast<long long>(n) + 16 * 256 - 1) / (16 * 256));
+    dequant_8bit_blockwise_kernel<T><<<grid, 256, 0, stream>>>(code, A, absmax, out, blocksize, n);
+  }
+}
+
+int launch_dequant_bnb4(const uint8_t* packed, const float* absmax, bf16* out, int blocksize, long long n, int is_nf4,
+                        cudaStream_t stream) {
+  FB_REQUIRE(blocksize >= 2 && blocksize % 2 == 0, "dequant_bnb4: bad blocksize");
+  const long long nbytes = (n + 1) / 2;
+  const unsigned grid = static_cast<unsigned>((nbytes + 16 * 256 - 1) / (16 * 256));
+  if (is_nf4)
+    dequant_4bit_kernel<bf16, 2><<<grid, 256, 0, stream>>>(packed, absmax, out, blocksize / 2, n);
+  else
+    dequant_4bit_kernel<bf16, 1><<<grid, 256, 0, stream>>>(packed, absmax, out, blocksize / 2, n);
+  FB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GGUF Q4_K: 256 weights per 144-byte super-block {f16 d, f16 dmin, 12 B packed 6-bit scales/mins, 128 B nibbles}
+// (diffusion_rs_common/src/core/quantized/k_quants.rs:130-136, to_float :1568-1599, get_scale_min_k4 utils.rs:49-59).
+// GgufMatMul::dequantize_w = dequantize (f32) -> f16 -> out dtype (gguf/mod.rs:29-31): both roundings are kept.
+// One warp per super-block; lane l expands bytes 4l..4l+3 of the 128 nibble bytes.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dequant_q4k_kernel(const uint8_t* __restrict__ blocks, bf16* __restrict__ out,
+                                                          long long nblocks) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long blk = blockIdx.x * 8LL + warp;
+  if (blk >= nblocks) return;
+  const uint8_t* p = blocks + blk * 144;
+  const float d = __half2float(*reinterpret_cast<const __half*>(p));
+  const float dmin = __half2float(*reinterpret_cast<const __half*>(p + 2));
+  const uint8_t* sc = p + 4;
+  const uint8_t* qs = p + 16;
+  // lane -> 64-weight group j = lane/8, 4 consecutive bytes inside the group's 32 bytes
+  const int j = lane >> 3;
+  const int off = (lane & 7) * 4;
+  auto scale_min = [&](int is, float& s, float& m) {
+    uint32_t dd, mm;
+    if (is < 4) {
+      dd = sc[is] & 63;
+      mm = sc[is + 4] & 63;
+    } else {
+      dd = (sc[is + 4] & 0xF) | ((sc[is - 4] >> 6) << 4);
+      mm = (sc[is + 4] >> 4) | ((sc[is] >> 6) << 4);
+    }
+    s = __fmul_rn(d, static_cast<float>(dd));
+    m = __fmul_rn(dmin, static_cast<float>(mm));
+  };
+  float d1, m1, d2, m2;
+  scale_min(2 * j, d1, m1);
+  scale_min(2 * j + 1, d2, m2);
+  const uint32_t q4 = *reinterpret_cast<const uint32_t*>(qs + j * 32 + off);
+  bf16* o = out + blk * 256 + j * 64 + off;
+  float lo[4], hi[4];
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    const uint32_t q = (q4 >> (8 * b)) & 0xff;
+    lo[b] = __half2float(__float2half_rn(__fsub_rn(__fmul_rn(d1, static_cast<float>(q & 0xF)), m1)));
+    hi[b] = __half2float(__float2half_rn(__fsub_rn(__fmul_rn(d2, static_cast<float>(q >> 4)), m2)));
+  }
+  uint2 u;
+  u.x = pack_bf16(lo[0], lo[1]), u.y = pack_bf16(lo[2], lo[3]);
+  *reinterpret_cast<uint2*>(o) = u;
+  u.x = pack_bf16(hi[0], hi[1]), u.y = pack_bf16(hi[2], hi[3]);
+  *reinterpret_cast<uint2*>(o + 32) = u;
+}
+
+int launch_dequant_q4k(const uint8_t* blocks, bf16* out, long long n, cudaStream_t stream) {
+  FB_REQUIRE(n % 256 == 0, "dequant_q4k: element count must be a multiple of 256");
+  const long long nblocks = n / 256;
+  dequant_q4k_kernel<<<static_cast<unsigned>((nblocks + 7) / 8), 256, 0, stream>>>(blocks, out, nblocks);
+  FB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace fb
+
+// ------------------------------------------------------------------------------------------------
+// The reference's FFI surface (same names, same argument lists, void return; bitsandbytes/ffi.rs:5-114)
+// ------------------------------------------------------------------------------------------------
+using fb::dequant_blockwise;
+extern "C" {
+#define FB_BNB(NAME, T, DT)                                                                                 \
+  void NAME(float* code, unsigned char* A, float* absmax, T* out, int blocksize, const int n, cudaStream_t stream) { \
+    dequant_blockwise<T, DT>(code, A, absmax, out, blocksize, n, stream);                                   \
+  }
+FB_BNB(dequantize_blockwise_f32_int8, float, 0)
+FB_BNB(dequantize_blockwise_f32_fp4, float, 1)
+FB_BNB(dequantize_blockwise_f32_nf4, float, 2)
+FB_BNB(dequantize_blockwise_f16_int8, __half, 0)
+FB_BNB(dequantize_blockwise_f16_fp4, __half, 1)
+FB_BNB(dequantize_blockwise_f16_nf4, __half, 2)
+FB_BNB(dequantize_blockwise_bf16_int8, __nv_bfloat16, 0)
+FB_BNB(dequantize_blockwise_bf16_fp4, __nv_bfloat16, 1)
+FB_BNB(dequantize_blockwise_bf16_nf4, __nv_bfloat16, 2)
+#undef FB_BNB
+
+#define FB_INT8(NAME, T)                                                                               \
+  void NAME(const int8_t* weight, const float* scb, T* out, const int row, const int col, const int n) { \
+    (void)row;                                                                                         \
+    if (n <= 0) return;                                                                                \
+    const unsigned grid = static_cast<unsigned>((static_cast<long long>(n) + 16 * 256 - 1) / (16 * 256)); \
+    fb::dequant_int8_rowwise_kernel<T><<<grid, 256, 0, 0>>>(weight, scb, out, col, n); /* legacy default stream, as the reference */ \
+  }
+FB_INT8(dequantize_8bit_kernel_f32, float)
+FB_INT8(dequantize_8bit_kernel_f16, __half)
+FB_INT8(dequantize_8bit_kernel_bf16, __nv_bfloat16)
+#undef FB_INT8
+}

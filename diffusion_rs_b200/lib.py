@@ -1,0 +1,73 @@
+"""ctypes binding of libfluxb200.so — the same C ABI a Rust `extern "C"` block would bind.
+
+PyTorch is used by callers only to own device memory and streams; every compute call goes through the C ABI.
+There is no CPU / eager fallback: if the library is missing or a call fails, a `Fluxb200Error` is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+_LIB_PATH = _PKG / "libfluxb200.so"
+_lib = None
+
+
+class Fluxb200Error(RuntimeError):
+    pass
+
+
+c_void_p, c_int, c_int64, c_float = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+
+# name -> (restype, argtypes); must list every symbol declared in include/fluxb200.h
+SIGNATURES = {
+    "fluxb200_last_error": (C.c_char_p, []),
+    "fluxb200_version": (c_int, []),
+    "fluxb200_linear": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_int,
+                                c_int, c_int, c_void_p, c_int64, c_int, c_void_p, c_float, c_void_p]),
+    "fluxb200_sdpa": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p]),
+    "fluxb200_layernorm_modulate": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int, c_int,
+                                            c_float, c_void_p]),
+    "fluxb200_qknorm_rope": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p]),
+}
+
+
+def lib_path() -> Path:
+    return _LIB_PATH
+
+
+def load() -> C.CDLL:
+    """Load the shared library (building is `diffusion_rs_b200.build.build()`); fails loudly if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIB_PATH.exists():
+        raise Fluxb200Error(
+            f"{_LIB_PATH} not found: build it with `python -m diffusion_rs_b200.build` (there is no CPU fallback)")
+    lib = C.CDLL(str(_LIB_PATH))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = load().fluxb200_last_error()
+        raise Fluxb200Error(msg.decode() if msg else f"fluxb200 call failed with status {rc}")
+
+
+def ptr(t) -> int | None:
+    """Device (or host) pointer of a torch tensor, None -> NULL."""
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def current_stream() -> int:
+    import torch
+
+    return torch.cuda.current_stream().cuda_stream
