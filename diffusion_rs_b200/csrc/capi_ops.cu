@@ -50,7 +50,7 @@ int fluxb200_qknorm_rope(const void* qkv, int64_t ld, int32_t batch, int32_t row
                          void* Q, void* K, void* V, float eps, fluxb200_stream_t stream) {
   return launch_qknorm_rope(static_cast<const bf16*>(qkv), ld, rows_per_batch, batch, H, L, l_off,
                             static_cast<const bf16*>(wq), static_cast<const bf16*>(wk),
-                            static_cast<const bf16*>(pe_cos), static_cast<const bf16*>(pe_sin), static_cast<bf16*>(Q),
+                            static_cast<const bf16*>(pe_cos), static_cast<const bf16*>(pe_sin), 0, static_cast<bf16*>(Q),
                             static_cast<bf16*>(K), static_cast<bf16*>(V), eps, static_cast<cudaStream_t>(stream));
 }
 

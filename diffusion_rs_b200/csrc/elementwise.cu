@@ -100,7 +100,8 @@ __global__ void __launch_bounds__(256) qknorm_rope_kernel(const bf16* __restrict
                                                           int rows_per_batch, int H, int L, int l_off,
                                                           const bf16* __restrict__ wq, const bf16* __restrict__ wk,
                                                           const bf16* __restrict__ pe_cos,
-                                                          const bf16* __restrict__ pe_sin, bf16* __restrict__ Q,
+                                                          const bf16* __restrict__ pe_sin, long long pe_bstride,
+                                                          bf16* __restrict__ Q,
                                                           bf16* __restrict__ K, bf16* __restrict__ V, float eps) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x;
@@ -128,8 +129,8 @@ __global__ void __launch_bounds__(256) qknorm_rope_kernel(const bf16* __restrict
 #pragma unroll
     for (int e = 0; e < 4; ++e) y[e] = rbf(rbf(x[e] / denom) * wf[e]);
     // rope: pairs (2i, 2i+1), i = lane*2 + {0,1}
-    const uint32_t cu = *reinterpret_cast<const uint32_t*>(pe_cos + static_cast<long long>(l) * 64 + lane * 2);
-    const uint32_t su = *reinterpret_cast<const uint32_t*>(pe_sin + static_cast<long long>(l) * 64 + lane * 2);
+    const uint32_t cu = *reinterpret_cast<const uint32_t*>(pe_cos + b * pe_bstride + static_cast<long long>(l) * 64 + lane * 2);
+    const uint32_t su = *reinterpret_cast<const uint32_t*>(pe_sin + b * pe_bstride + static_cast<long long>(l) * 64 + lane * 2);
     const float c[2] = {bf_lo(cu), bf_hi(cu)};
     const float s[2] = {bf_lo(su), bf_hi(su)};
     float o[4];
@@ -147,11 +148,11 @@ __global__ void __launch_bounds__(256) qknorm_rope_kernel(const bf16* __restrict
 }
 
 int launch_qknorm_rope(const bf16* qkv, long long ld, int rows_per_batch, int batch, int H, int L, int l_off,
-                       const bf16* wq, const bf16* wk, const bf16* pe_cos, const bf16* pe_sin, bf16* Q, bf16* K,
-                       bf16* V, float eps, cudaStream_t stream) {
+                       const bf16* wq, const bf16* wk, const bf16* pe_cos, const bf16* pe_sin, long long pe_bstride,
+                       bf16* Q, bf16* K, bf16* V, float eps, cudaStream_t stream) {
   const int rows = rows_per_batch * batch;
-  qknorm_rope_kernel<<<rows, 256, 0, stream>>>(qkv, ld, rows_per_batch, H, L, l_off, wq, wk, pe_cos, pe_sin, Q, K, V,
-                                               eps);
+  qknorm_rope_kernel<<<rows, 256, 0, stream>>>(qkv, ld, rows_per_batch, H, L, l_off, wq, wk, pe_cos, pe_sin,
+                                               pe_bstride, Q, K, V, eps);
   FB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -163,8 +164,9 @@ int launch_qknorm_rope(const bf16* qkv, long long ld, int rows_per_batch, int ba
 // HBM-bound on the weights: one warp per output row streams W[n, :] once with 16-byte loads, x lives in smem.
 // ------------------------------------------------------------------------------------------------
 template <int BMAX>
-__global__ void __launch_bounds__(256) gemv_jobs_kernel(const GemvJob* __restrict__ jobs, int njobs, int total_rows,
-                                                        const bf16* __restrict__ x, long long x_ld, int B, int K) {
+__global__ void __launch_bounds__(256) gemv_jobs_kernel(const GemvJob* __restrict__ jobs, int njobs, int row_base,
+                                                        int total_rows, const bf16* __restrict__ x, long long x_ld,
+                                                        int B, int K, bf16* __restrict__ out_base) {
   extern __shared__ uint8_t smem_raw[];
   bf16* xs = reinterpret_cast<bf16*>(smem_raw);  // [B][K]
   for (int i = threadIdx.x; i < B * (K / 8); i += blockDim.x) {
@@ -176,8 +178,8 @@ __global__ void __launch_bounds__(256) gemv_jobs_kernel(const GemvJob* __restric
   constexpr int ROWS_PER_WARP = 4;
   const int row0 = (blockIdx.x * 8 + warp) * ROWS_PER_WARP;
   for (int rr = 0; rr < ROWS_PER_WARP; ++rr) {
-    const int grow = row0 + rr;
-    if (grow >= total_rows) return;
+    if (row0 + rr >= total_rows) return;
+    const int grow = row_base + row0 + rr;
     int lo = 0, hi = njobs - 1;  // last job with row_begin <= grow
     while (lo < hi) {
       const int mid = (lo + hi + 1) >> 1;
@@ -209,17 +211,22 @@ __global__ void __launch_bounds__(256) gemv_jobs_kernel(const GemvJob* __restric
 #pragma unroll
       for (int b = 0; b < BMAX; ++b) {
         if (b < B) {
-          float v = rbf(acc[b]);
-          if (job.bias) v = rbf(v + bias);
-          job.out[b * job.out_ld + n] = __float2bfloat16_rn(v);
+          float v;
+          if (job.bias && job.fused_bias) {
+            v = rbf(acc[b] + bias);
+          } else {
+            v = rbf(acc[b]);
+            if (job.bias) v = rbf(v + bias);
+          }
+          out_base[job.out_off + b * job.out_ld + n] = __float2bfloat16_rn(v);
         }
       }
     }
   }
 }
 
-int launch_gemv_jobs(const GemvJob* jobs_dev, int njobs, int total_rows, const bf16* x, long long x_ld, int B, int K,
-                     cudaStream_t stream) {
+int launch_gemv_jobs(const GemvJob* jobs_dev, int njobs, int row_base, int total_rows, const bf16* x, long long x_ld,
+                     int B, int K, bf16* out_base, cudaStream_t stream) {
   FB_REQUIRE(B >= 1 && B <= 8, "gemv_jobs: batch must be in 1..8");
   FB_REQUIRE(K % 8 == 0, "gemv_jobs: K must be a multiple of 8");
   const size_t smem = static_cast<size_t>(B) * K * 2;
@@ -231,14 +238,14 @@ int launch_gemv_jobs(const GemvJob* jobs_dev, int njobs, int total_rows, const b
       FB_CHECK_CUDA(cudaFuncSetAttribute(gemv_jobs_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
       set2 = true;
     }
-    gemv_jobs_kernel<2><<<grid, 256, smem, stream>>>(jobs_dev, njobs, total_rows, x, x_ld, B, K);
+    gemv_jobs_kernel<2><<<grid, 256, smem, stream>>>(jobs_dev, njobs, row_base, total_rows, x, x_ld, B, K, out_base);
   } else {
     static bool set8 = false;
     if (!set8) {
       FB_CHECK_CUDA(cudaFuncSetAttribute(gemv_jobs_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
       set8 = true;
     }
-    gemv_jobs_kernel<8><<<grid, 256, smem, stream>>>(jobs_dev, njobs, total_rows, x, x_ld, B, K);
+    gemv_jobs_kernel<8><<<grid, 256, smem, stream>>>(jobs_dev, njobs, row_base, total_rows, x, x_ld, B, K, out_base);
   }
   FB_CHECK_CUDA(cudaGetLastError());
   return 0;

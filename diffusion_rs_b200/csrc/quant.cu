@@ -146,6 +146,13 @@ int launch_dequant_bnb4(const uint8_t* packed, const float* absmax, bf16* out, i
   return 0;
 }
 
+int launch_dequant_int8(const int8_t* w, const float* scb, bf16* out, int col, long long n, cudaStream_t stream) {
+  const unsigned grid = static_cast<unsigned>((n + 16 * 256 - 1) / (16 * 256));
+  dequant_int8_rowwise_kernel<bf16><<<grid, 256, 0, stream>>>(w, scb, out, col, n);
+  FB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // GGUF Q4_K: 256 weights per 144-byte super-block {f16 d, f16 dmin, 12 B packed 6-bit scales/mins, 128 B nibbles}
 // (diffusion_rs_common/src/core/quantized/k_quants.rs:130-136, to_float :1568-1599, get_scale_min_k4 utils.rs:49-59).

@@ -30,7 +30,50 @@ SIGNATURES = {
                                             c_float, c_void_p]),
     "fluxb200_qknorm_rope": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p]),
+    # the reference's own FFI surface (bitsandbytes/ffi.rs:5-114)
+    **{f"dequantize_blockwise_{t}_{q}": (None, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p])
+       for t in ("f32", "f16", "bf16") for q in ("int8", "fp4", "nf4")},
+    **{f"dequantize_8bit_kernel_{t}": (None, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int])
+       for t in ("f32", "f16", "bf16")},
+    "fluxb200_dequantize_q4k_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    # model level
+    "fluxb200_model_create": (c_int, [c_void_p, C.POINTER(c_void_p)]),
+    "fluxb200_model_destroy": (None, [c_void_p]),
+    "fluxb200_model_load_weight": (c_int, [c_void_p, C.c_char_p, c_void_p, c_int, C.POINTER(c_int64), c_int, c_int,
+                                           c_void_p]),
+    "fluxb200_model_finalize": (c_int, [c_void_p, c_void_p]),
+    "fluxb200_model_workspace_size": (c_int, [c_void_p, c_int, c_int, c_int, C.POINTER(C.c_uint64)]),
+    "fluxb200_model_forward": (c_int, [c_void_p] + [c_void_p] * 8 + [c_int, c_int, c_int, c_void_p, C.c_uint64,
+                                                                      c_void_p]),
+    "fluxb200_model_denoise": (c_int, [c_void_p] + [c_void_p] * 5 + [c_float, C.POINTER(C.c_double), c_int, c_int,
+                                                                      c_int, c_int, c_void_p, C.c_uint64, c_void_p]),
+    "fluxb200_model_tap": (c_int, [c_void_p, c_int, c_void_p, C.c_uint64, c_void_p]),
+    # VAE
+    "fluxb200_vae_create": (c_int, [c_void_p, C.POINTER(c_void_p)]),
+    "fluxb200_vae_destroy": (None, [c_void_p]),
+    "fluxb200_vae_load_weight": (c_int, [c_void_p, C.c_char_p, c_void_p, c_int, C.POINTER(c_int64), c_int, c_int,
+                                         c_void_p]),
+    "fluxb200_vae_finalize": (c_int, [c_void_p, c_void_p]),
+    "fluxb200_vae_workspace_size": (c_int, [c_void_p, c_int, c_int, c_int, C.POINTER(C.c_uint64)]),
+    "fluxb200_vae_decode": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, C.c_uint64,
+                                    c_void_p]),
+    "fluxb200_vae_decode_packed_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                                              C.c_uint64, c_void_p]),
+    "fluxb200_conv2d_nhwc": (c_int, [c_void_p] * 5 + [c_int] * 6 + [c_void_p]),
+    "fluxb200_repack_conv_weight": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "fluxb200_groupnorm_nhwc": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_float, c_int, c_void_p, c_void_p]),
 }
+
+
+class VaeConfigC(C.Structure):
+    _fields_ = [("latent_channels", c_int), ("out_channels", c_int), ("block_out_channels", c_int * 4),
+                ("layers_per_block", c_int), ("norm_num_groups", c_int), ("mid_block_add_attention", c_int),
+                ("scaling_factor", c_float), ("shift_factor", c_float)]
+
+
+class FluxConfigC(C.Structure):
+    _fields_ = [(n, c_int) for n in ("in_channels", "pooled_projection_dim", "joint_attention_dim",
+                                     "num_attention_heads", "num_layers", "num_single_layers", "guidance_embeds")]
 
 
 def lib_path() -> Path:

@@ -64,6 +64,141 @@ int fluxb200_qknorm_rope(const void* qkv, int64_t ld, int32_t batch, int32_t row
                          int32_t l_off, const void* wq, const void* wk, const void* pe_cos, const void* pe_sin,
                          void* Q, void* K, void* V, float eps, fluxb200_stream_t stream);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * The 12 symbols of the reference's existing FFI, same names and argument lists
+ * (diffusion_rs_backend/src/bitsandbytes/ffi.rs:5-114; C side kernels/bitsandbytes/dequant.cu:172-232).
+ * `stream` is a CUstream; the dequantize_8bit_kernel_* family runs on the legacy default stream as in the reference.
+ * ---------------------------------------------------------------------------------------------- */
+void dequantize_blockwise_f32_int8(float* code, unsigned char* a, float* absmax, float* out, int blocksize, int n, fluxb200_stream_t stream);
+void dequantize_blockwise_f32_fp4(float* code, unsigned char* a, float* absmax, float* out, int blocksize, int n, fluxb200_stream_t stream);
+void dequantize_blockwise_f32_nf4(float* code, unsigned char* a, float* absmax, float* out, int blocksize, int n, fluxb200_stream_t stream);
+void dequantize_blockwise_f16_int8(float* code, unsigned char* a, float* absmax, void* out, int blocksize, int n, fluxb200_stream_t stream);
+void dequantize_blockwise_f16_fp4(float* code, unsigned char* a, float* absmax, void* out, int blocksize, int n, fluxb200_stream_t stream);
+void dequantize_blockwise_f16_nf4(float* code, unsigned char* a, float* absmax, void* out, int blocksize, int n, fluxb200_stream_t stream);
+void dequantize_blockwise_bf16_int8(float* code, unsigned char* a, float* absmax, void* out, int blocksize, int n, fluxb200_stream_t stream);
+void dequantize_blockwise_bf16_fp4(float* code, unsigned char* a, float* absmax, void* out, int blocksize, int n, fluxb200_stream_t stream);
+void dequantize_blockwise_bf16_nf4(float* code, unsigned char* a, float* absmax, void* out, int blocksize, int n, fluxb200_stream_t stream);
+void dequantize_8bit_kernel_f32(const int8_t* weight, const float* scb, float* out, int row, int col, int n);
+void dequantize_8bit_kernel_f16(const int8_t* weight, const float* scb, void* out, int row, int col, int n);
+void dequantize_8bit_kernel_bf16(const int8_t* weight, const float* scb, void* out, int row, int col, int n);
+
+/* GGUF Q4_K super-blocks (144 B / 256 weights) -> bf16, the `dequantize_w` semantics of GgufMatMul
+ * (diffusion_rs_backend/src/gguf/mod.rs:29-31; k_quants.rs:1568-1599): f32 -> f16 -> bf16. n = element count. */
+int fluxb200_dequantize_q4k_bf16(const void* blocks, void* out, int64_t n, fluxb200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Model-level entry points: the FLUX transformer behind Flux::new / Flux::forward (models/flux/model.rs:722-833)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct fluxb200_model fluxb200_model;
+
+typedef struct {
+  int32_t in_channels;           /* 64 */
+  int32_t pooled_projection_dim; /* 768 */
+  int32_t joint_attention_dim;   /* 4096 */
+  int32_t num_attention_heads;   /* 24 */
+  int32_t num_layers;            /* 19 double-stream blocks */
+  int32_t num_single_layers;     /* 38 single-stream blocks */
+  int32_t guidance_embeds;       /* 1 for FLUX.1-dev, 0 for schnell */
+} fluxb200_flux_config; /* == models/flux/model.rs:21-31 Config (quantization is sniffed from tensor names) */
+
+/* tensor dtypes accepted by fluxb200_load_weight */
+#define FLUXB200_DT_BF16 0
+#define FLUXB200_DT_F32 1
+#define FLUXB200_DT_U8 2
+#define FLUXB200_DT_I8 3
+#define FLUXB200_DT_F16 4
+#define FLUXB200_DT_Q4K 10 /* GGUF Q4_K blocks; shape = logical [out, in] */
+
+int fluxb200_model_create(const fluxb200_flux_config* cfg, fluxb200_model** out);
+void fluxb200_model_destroy(fluxb200_model* m);
+
+/* Hand one checkpoint tensor to the model under its diffusers name (what VarBuilder::get resolves in the reference,
+ * e.g. "transformer_blocks.0.attn.to_q.weight", "...weight.absmax", "...weight.quant_state.bitsandbytes__nf4",
+ * "...SCB").  `data` may be a host or a device pointer (is_device != 0).  The bytes are copied; the caller keeps
+ * ownership of `data`. */
+int fluxb200_model_load_weight(fluxb200_model* m, const char* name, const void* data, int32_t dtype,
+                               const int64_t* shape, int32_t rank, int32_t is_device, fluxb200_stream_t stream);
+
+/* After the last tensor: checks that every tensor Flux::new would `vb.get` is present, picks dense / bnb / gguf per
+ * layer exactly like diffusion_rs_backend::linear* (lib.rs:197-266) and repacks into the kernel layouts. */
+int fluxb200_model_finalize(fluxb200_model* m, fluxb200_stream_t stream);
+
+/* Bytes of caller-owned workspace one forward needs for this problem size. */
+int fluxb200_model_workspace_size(const fluxb200_model* m, int32_t batch, int32_t l_img, int32_t l_txt,
+                                  uint64_t* bytes);
+
+/* Flux::forward (model.rs:790-833).  All tensors are device pointers:
+ *   img bf16 [B,l_img,64]; img_ids bf16 [B,l_img,3]; txt bf16 [B,l_txt,4096]; txt_ids bf16 [B,l_txt,3];
+ *   timesteps f32 [B]; y bf16 [B,768]; guidance f32 [B] or NULL; out bf16 [B,l_img,64]. */
+int fluxb200_model_forward(fluxb200_model* m, const void* img, const void* img_ids, const void* txt,
+                           const void* txt_ids, const void* timesteps, const void* y, const void* guidance,
+                           void* out, int32_t batch, int32_t l_img, int32_t l_txt, void* workspace,
+                           uint64_t workspace_bytes, fluxb200_stream_t stream);
+
+/* Sampler::sample (pipelines/sampling.rs:25-48): the Euler flow-matching loop over `timesteps` (host f64[n_t]),
+ * updating `img` in place; txt projection and the RoPE table are hoisted out of the loop (they do not depend on t). */
+int fluxb200_model_denoise(fluxb200_model* m, void* img, const void* img_ids, const void* txt, const void* txt_ids,
+                           const void* y, float guidance_scale, const double* timesteps, int32_t n_timesteps,
+                           int32_t batch, int32_t l_img, int32_t l_txt, void* workspace, uint64_t workspace_bytes,
+                           fluxb200_stream_t stream);
+
+/* Debug / parity taps: copy an internal activation of the last forward into `out` (device, bf16).
+ * which: 0 = vec_ [B,3072], 1 = img stream after the double blocks [B,l_img,3072], 2 = txt stream [B,l_txt,3072],
+ *        3 = joint stream after the single blocks [B,l,3072], 4 = pe_cos [B,l,64], 5 = pe_sin [B,l,64]. */
+int fluxb200_model_tap(fluxb200_model* m, int32_t which, void* out, uint64_t out_bytes, fluxb200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * VAE decode: AutoEncoderKl::decode -> Decoder::forward (models/vaes/autoencoder_kl.rs:112-119, vae.rs:437-455)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct fluxb200_vae fluxb200_vae;
+
+typedef struct {
+  int32_t latent_channels;       /* 16 */
+  int32_t out_channels;          /* 3 */
+  int32_t block_out_channels[4]; /* 128, 256, 512, 512 */
+  int32_t layers_per_block;      /* 2 */
+  int32_t norm_num_groups;       /* 32 */
+  int32_t mid_block_add_attention;
+  float scaling_factor;          /* 0.3611 */
+  float shift_factor;            /* 0.1159 */
+} fluxb200_vae_config; /* == autoencoder_kl.rs:15-32 (decoder-relevant fields) */
+
+int fluxb200_vae_create(const fluxb200_vae_config* cfg, fluxb200_vae** out);
+void fluxb200_vae_destroy(fluxb200_vae* v);
+/* Tensor names as the reference resolves them under the `decoder` prefix (vae.rs:371-433), e.g.
+ * "decoder.up_blocks.0.resnets.1.conv1.weight" [Cout,Cin,3,3], "decoder.mid_block.attentions.0.to_q.weight" [512,512]. */
+int fluxb200_vae_load_weight(fluxb200_vae* v, const char* name, const void* data, int32_t dtype, const int64_t* shape,
+                             int32_t rank, int32_t is_device, fluxb200_stream_t stream);
+int fluxb200_vae_finalize(fluxb200_vae* v, fluxb200_stream_t stream);
+int fluxb200_vae_workspace_size(const fluxb200_vae* v, int32_t batch, int32_t h, int32_t w, uint64_t* bytes);
+
+/* VAEModel::decode: z bf16 NCHW [B, 16, h, w] -> out bf16 NCHW [B, 3, 8h, 8w]. */
+int fluxb200_vae_decode(fluxb200_vae* v, const void* z, void* out, int32_t batch, int32_t h, int32_t w,
+                        void* workspace, uint64_t workspace_bytes, fluxb200_stream_t stream);
+
+/* Tail of FluxPipeline::forward (pipelines/flux/mod.rs:327-332): unpack the packed latents [B, h2*w2, 64], apply
+ * z/scaling_factor + shift_factor, decode, clamp(-1,1) -> (x+1)*127.5 -> u8.  out is [B, 16*h2, 16*w2, 3] (image
+ * layout) when nchw == 0, or the reference tensor layout [B, 3, 16*h2, 16*w2] when nchw != 0. */
+int fluxb200_vae_decode_packed_u8(fluxb200_vae* v, const void* packed, void* out_u8, int32_t batch, int32_t h2,
+                                  int32_t w2, int32_t nchw, void* workspace, uint64_t workspace_bytes,
+                                  fluxb200_stream_t stream);
+
+/* Operator-level: 2-D convolution on NHWC bf16 activations, stride 1, padding k/2, k in {1,3}; weight is the
+ * repacked [Cout, k, k, Cin] tensor.  out = bf16(bf16(conv) + bias) (+ res).  Replaces Conv2d::forward
+ * (nn/conv.rs:212-230 -> cuda_backend/mod.rs:1545-1599) without materialising an im2col buffer. */
+int fluxb200_conv2d_nhwc(const void* x, const void* w_packed, const void* bias, const void* res, void* out,
+                         int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t ksize,
+                         fluxb200_stream_t stream);
+/* Repack a conv weight [Cout, Cin, k, k] -> [Cout, k, k, Cin]. */
+int fluxb200_repack_conv_weight(const void* w, void* out, int32_t Cout, int32_t Cin, int32_t ksize,
+                                fluxb200_stream_t stream);
+/* GroupNorm (32 groups) + optional SiLU on NHWC bf16; stats_scratch: >= N*32*2 doubles of device memory.
+ * Replaces nn::GroupNorm::forward (nn/group_norm.rs:39-74) (+ Activation::Silu). */
+int fluxb200_groupnorm_nhwc(const void* x, const void* weight, const void* bias, void* out, int32_t N, int32_t HW,
+                            int32_t C, int32_t groups, float eps, int32_t silu, void* stats_scratch,
+                            fluxb200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

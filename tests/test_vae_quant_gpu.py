@@ -1,0 +1,240 @@
+"""GPU parity: VAE decode (C ABI fluxb200_vae_*) and quantised-weight paths vs the oracle."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import flux as OF
+from oracle import ops as O
+from oracle import quant as Q
+from oracle import vae as OV
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# conv / groupnorm operator level
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,H,W,Cin,Cout,k", [(1, 16, 16, 64, 128, 3), (2, 13, 20, 128, 64, 3), (1, 8, 24, 16, 512, 3),
+                                              (1, 32, 32, 128, 3, 3), (1, 9, 16, 256, 128, 1)])
+def test_conv2d_nhwc(fluxlib, N, H, W, Cin, Cout, k):
+    from diffusion_rs_b200 import lib as L
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(N, Cin, H, W, generator=g).bfloat16()
+    w = (torch.randn(Cout, Cin, k, k, generator=g) / math.sqrt(Cin * k * k)).bfloat16()
+    b = (0.1 * torch.randn(Cout, generator=g)).bfloat16()
+    ref = O.rb(O.rb(torch.nn.functional.conv2d(x.float(), w.float(), None, padding=k // 2)) + b.float()[None, :, None, None])
+    xd = x.permute(0, 2, 3, 1).contiguous().cuda()
+    wd = w.cuda()
+    wp = torch.empty(Cout, k, k, Cin, device="cuda", dtype=torch.bfloat16)
+    L.check(fluxlib.fluxb200_repack_conv_weight(wd.data_ptr(), wp.data_ptr(), Cout, Cin, k, L.current_stream()))
+    assert torch.equal(wp.cpu(), w.permute(0, 2, 3, 1).contiguous())
+    out = torch.empty(N, H, W, Cout, device="cuda", dtype=torch.bfloat16)
+    L.check(fluxlib.fluxb200_conv2d_nhwc(xd.data_ptr(), wp.data_ptr(), b.cuda().data_ptr(), None, out.data_ptr(), N, H,
+                                         W, Cin, Cout, k, L.current_stream()))
+    got = out.permute(0, 3, 1, 2).float().cpu()
+    assert _rel(got, ref) < 2e-3
+    assert (got != ref).float().mean().item() < 0.02
+
+
+@pytest.mark.parametrize("N,HW,C,silu", [(2, 300, 512, 1), (1, 4096, 128, 1), (1, 1000, 256, 0)])
+def test_groupnorm_nhwc(fluxlib, N, HW, C, silu):
+    from diffusion_rs_b200 import lib as L
+    g = torch.Generator().manual_seed(4)
+    x = (torch.randn(N, C, HW, generator=g) * 2 + 0.5).bfloat16()
+    w = (1 + 0.1 * torch.randn(C, generator=g)).bfloat16()
+    b = (0.1 * torch.randn(C, generator=g)).bfloat16()
+    ref = O.group_norm(x.float(), w.float(), b.float(), 32, 1e-6)
+    if silu:
+        ref = O.silu(ref)
+    xd = x.permute(0, 2, 1).contiguous().cuda()
+    out = torch.empty_like(xd)
+    stats = torch.zeros(N * 64, dtype=torch.float64, device="cuda")
+    L.check(fluxlib.fluxb200_groupnorm_nhwc(xd.data_ptr(), w.cuda().data_ptr(), b.cuda().data_ptr(), out.data_ptr(), N,
+                                            HW, C, 32, 1e-6, silu, stats.data_ptr(), L.current_stream()))
+    got = out.permute(0, 2, 1).float().cpu()
+    assert (got != ref).float().mean().item() < 5e-3
+    assert _rel(got, ref) < 1e-3
+
+
+# ---------------------------------------------------------------------------------------------------------
+# VAE decode
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,h,w", [(1, 16, 16), (2, 10, 12)])
+def test_vae_decode_vs_oracle(fluxlib, B, h, w):
+    from diffusion_rs_b200.vae import AutoEncoderKl, VaeConfig
+    cfg = OV.VaeConfig()
+    W = OV.make_weights(cfg)
+    vae = AutoEncoderKl.new(VaeConfig(), {k: v.cuda() for k, v in W.items()})
+    z = torch.randn(B, 16, h, w, generator=torch.Generator().manual_seed(9)).bfloat16()
+    out = vae.decode(z.cuda())
+    torch.cuda.synchronize()
+    ref = OV.VaeOracle(cfg, W, O.REF).decode(z.float())
+    tru = OV.VaeOracle(cfg, W, O.F32).decode(z.float())
+    e1, e2, e3 = _rel(out, ref), _rel(out, tru), _rel(ref, tru)
+    print(f"\nVAE decode B={B} {h}x{w}: |ours-ref|={e1:.3e} |ours-f32|={e2:.3e} |ref-f32|={e3:.3e}")
+    assert e1 < 3e-2
+    assert e2 < 1.5 * e3 + 1e-3
+
+
+def test_vae_packed_u8(fluxlib):
+    from diffusion_rs_b200.vae import AutoEncoderKl, VaeConfig
+    cfg = OV.VaeConfig()
+    W = OV.make_weights(cfg)
+    vae = AutoEncoderKl.new(VaeConfig(), {k: v.cuda() for k, v in W.items()})
+    B, h2, w2 = 1, 6, 8
+    packed = torch.randn(B, h2 * w2, 64, generator=torch.Generator().manual_seed(10)).bfloat16()
+    img = vae.decode_packed_u8(packed.cuda(), h2, w2)  # [B, H, W, 3]
+    ref = OV.VaeOracle(cfg, W, O.REF).decode_packed_u8(packed.float(), 16 * h2, 16 * w2)  # [B,3,H,W]
+    got = img.permute(0, 3, 1, 2).cpu().int()
+    d = (got - ref.int()).abs()
+    print(f"\nu8 image: mean abs diff {d.float().mean():.3f}, max {d.max().item()}, exact {(d == 0).float().mean():.3f}")
+    assert d.float().mean().item() < 1.5
+    nchw = vae.decode_packed_u8(packed.cuda(), h2, w2, nchw=True)
+    assert torch.equal(nchw.cpu(), img.permute(0, 3, 1, 2).cpu())
+
+
+# ---------------------------------------------------------------------------------------------------------
+# quantised formats
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["nf4", "fp4"])
+@pytest.mark.parametrize("ty", ["f32", "f16", "bf16"])
+def test_bnb_4bit_ffi_symbols(fluxlib, kind, ty):
+    """The reference's own FFI symbols (bitsandbytes/ffi.rs) produce the oracle's bytes exactly."""
+    from diffusion_rs_b200 import lib as L
+    rs = np.random.RandomState(1)
+    n, bs = 64 * 1000 + 0, 64
+    w = rs.randn(n).astype(np.float32)
+    packed, absmax = Q.quantize_4bit(w, bs, kind)
+    ref = Q.dequant_4bit(packed, absmax, bs, n, kind)
+    tdt = {"f32": torch.float32, "f16": torch.float16, "bf16": torch.bfloat16}[ty]
+    out = torch.empty(n, dtype=tdt, device="cuda")
+    code = torch.zeros(16, dtype=torch.float32, device="cuda")
+    fn = getattr(fluxlib, f"dequantize_blockwise_{ty}_{kind}")
+    fn(code.data_ptr(), torch.from_numpy(packed).cuda().data_ptr(), torch.from_numpy(absmax).cuda().data_ptr(),
+       out.data_ptr(), bs, n, L.current_stream())
+    torch.cuda.synchronize()
+    assert torch.equal(out.cpu(), torch.from_numpy(ref).to(tdt))
+
+
+def test_bnb_int8_ffi_symbols(fluxlib):
+    from diffusion_rs_b200 import lib as L
+    rs = np.random.RandomState(2)
+    # blockwise 8-bit with a code book (nested absmax path)
+    n, bs = 4096 * 3 + 17, 256
+    q = rs.randint(0, 256, n).astype(np.uint8)
+    code = np.sort(rs.randn(256)).astype(np.float32)
+    absmax = np.abs(rs.randn((n + bs - 1) // bs)).astype(np.float32)
+    ref = Q.dequant_blockwise_int8(code, q, absmax, bs)
+    out = torch.empty(n, dtype=torch.float32, device="cuda")
+    fluxlib.dequantize_blockwise_f32_int8(torch.from_numpy(code).cuda().data_ptr(), torch.from_numpy(q).cuda().data_ptr(),
+                                          torch.from_numpy(absmax).cuda().data_ptr(), out.data_ptr(), bs, n,
+                                          L.current_stream())
+    torch.cuda.synchronize()
+    assert torch.equal(out.cpu(), torch.from_numpy(ref))
+    # LLM.int8 row-wise
+    rows, cols = 37, 96
+    w8 = rs.randint(-127, 128, (rows, cols)).astype(np.int8)
+    scb = np.abs(rs.randn(rows)).astype(np.float32)
+    ref = Q.dequant_int8_rowwise(w8, scb)
+    out = torch.empty(rows, cols, dtype=torch.bfloat16, device="cuda")
+    torch.cuda.synchronize()
+    fluxlib.dequantize_8bit_kernel_bf16(torch.from_numpy(w8).cuda().data_ptr(), torch.from_numpy(scb).cuda().data_ptr(),
+                                        out.data_ptr(), rows, cols, rows * cols)
+    torch.cuda.synchronize()
+    assert torch.equal(out.cpu(), torch.from_numpy(ref).bfloat16())
+
+
+def test_q4k_dequant(fluxlib):
+    from diffusion_rs_b200 import lib as L
+    rs = np.random.RandomState(3)
+    w = rs.randn(64, 1024).astype(np.float32)
+    blocks = Q.quantize_q4k(w)
+    ref = Q.dequant_q4k_bf16(blocks).reshape(64, 1024)
+    out = torch.empty(64, 1024, dtype=torch.bfloat16, device="cuda")
+    L.check(fluxlib.fluxb200_dequantize_q4k_bf16(torch.from_numpy(blocks).cuda().data_ptr(), out.data_ptr(), 64 * 1024,
+                                                 L.current_stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(out.float().cpu(), torch.from_numpy(ref))
+
+
+def _quantize_model_weights(weights, kind):
+    """Replace every block Linear weight by its quantised form; returns (tensors, dequantised dict)."""
+    tensors, deq = {}, {}
+    for name, t in weights.items():
+        is_block_linear = name.endswith(".weight") and t.dim() == 2 and ("transformer_blocks" in name)
+        if not is_block_linear:
+            tensors[name] = t
+            deq[name] = t
+            continue
+        w = t.float().numpy()
+        N, K = w.shape
+        if kind == "q4k":
+            blocks = Q.quantize_q4k(w)
+            tensors[name] = ("q4k", torch.from_numpy(blocks.reshape(-1)), (N, K))
+            deq[name] = torch.from_numpy(Q.dequant_q4k_bf16(blocks).reshape(N, K)).bfloat16()
+        else:
+            packed, absmax = Q.quantize_4bit(w, 64, "nf4")
+            a8, ncode, nabs, off = Q.quantize_absmax_nested(absmax, 256)
+            am = Q.nested_absmax(a8, ncode, nabs, 256, off)
+            prefix = name  # "...weight"
+            tensors[name] = torch.from_numpy(packed.reshape(-1, 1))
+            tensors[prefix + ".absmax"] = torch.from_numpy(a8)
+            tensors[prefix + ".quant_map"] = torch.from_numpy(Q.NF4_LUT.copy())
+            tensors[prefix + ".nested_absmax"] = torch.from_numpy(nabs)
+            tensors[prefix + ".nested_quant_map"] = torch.from_numpy(ncode)
+            js = Q.quant_state_json(64, (N, K), 256, off)
+            tensors[prefix + ".quant_state.bitsandbytes__nf4"] = torch.from_numpy(np.frombuffer(js, dtype=np.uint8).copy())
+            d = Q.dequant_4bit(packed, am, 64, N * K, "nf4").reshape(N, K)
+            deq[name] = torch.from_numpy(Q.bf16_round(d)).bfloat16()
+    return tensors, deq
+
+
+@pytest.mark.parametrize("kind", ["nf4", "q4k"])
+def test_quantised_dit_step(fluxlib, kind):
+    """C3 / C5 semantics at reduced depth: oracle weight = dequant(quant(W)); bnb adds the bias after rounding."""
+    from diffusion_rs_b200.transformer import DT_Q4K, FluxConfig, FluxTransformer
+    cfg = OF.FluxConfig(num_layers=1, num_single_layers=1, guidance_embeds=True)
+    weights = OF.make_weights(cfg)
+    tensors, deq = _quantize_model_weights(weights, kind)
+    m = FluxTransformer(FluxConfig(num_layers=1, num_single_layers=1, guidance_embeds=True))
+    for name, t in tensors.items():
+        if isinstance(t, tuple):
+            m.load_weight(name, t[1].cuda(), DT_Q4K, t[2])
+        else:
+            m.load_weight(name, t.cuda())
+    m.finalize()
+    B, h2, w2, l_txt = 1, 8, 8, 64
+    g = torch.Generator().manual_seed(11)
+    img = torch.randn(B, h2 * w2, 64, generator=g).bfloat16()
+    txt = torch.randn(B, l_txt, 4096, generator=g).bfloat16()
+    y = torch.randn(B, 768, generator=g).bfloat16()
+    ids = OF.make_ids(h2, w2, l_txt)
+    idb = ids.bfloat16()
+    t = torch.tensor([0.6])
+    gd = torch.tensor([3.5])
+    out = m.forward(img.cuda(), idb[l_txt:][None].contiguous().cuda(), txt.cuda(), idb[:l_txt][None].contiguous().cuda(), t,
+                    y.cuda(), gd)
+    torch.cuda.synchronize()
+
+    class QOracle(OF.FluxOracle):
+        def lin3(self, x, name):
+            quant = "transformer_blocks" in name
+            fused = (kind == "q4k") or not quant  # bnb: separate bf16 add (bitsandbytes/mod.rs:301-312)
+            return O.linear(x, self.w[name + ".weight"], self.w[name + ".bias"], fused_bias=fused, mode=self.mode)
+
+        def lin2(self, x, name):
+            quant = "transformer_blocks" in name
+            fused = (kind == "q4k") and quant  # gguf: f32 matmul + f32 bias, one rounding (gguf/mod.rs:33-40)
+            return O.linear(x, self.w[name + ".weight"], self.w[name + ".bias"], fused_bias=fused, mode=self.mode)
+
+    ref = QOracle(cfg, deq, O.REF).forward(img.float(), ids, txt.float(), t, y.float(), gd)
+    e = _rel(out, ref)
+    print(f"\n{kind} DiT step: rel err {e:.3e}")
+    assert e < 3e-2
