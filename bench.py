@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py — images/sec of the FLUX.1-dev 1024x1024 50-step bf16 hot path (BASELINE.json metric) on N B200s.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (sm_100a kernels through the C ABI)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on host cores
+
+A "step" is ONE IMAGE per GPU: 50 DiT denoising steps + the VAE decode (configs[1] of BASELINE.json).  For N > 1 the
+driver launches this file under torchrun; prompts are sharded one per rank (weak scaling, no per-step collective).
+Timing: W untimed images, then exactly K images bracketed by barrier + synchronize, CUDA events, max over ranks.
+  value : device-resident inputs (latents/embeddings already in HBM)            -> images/s, whole job
+  e2e   : Pipeline.forward with HOST buffers (pinned H2D of embeddings + noise, D2H of the u8 image inside the
+          timed region)                                                            -> images/s, whole job
+Weights and inputs are synthetic (random-init FLUX.1-dev architecture; no network / checkpoints in this environment).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "images/sec FLUX.1-dev 1024x1024 50-step bf16"
+UNIT = "images/s"
+HEIGHT = WIDTH = 1024
+NUM_STEPS = 50
+GUIDANCE = 3.5
+L_TXT = 512
+# algorithmic work: GEMM-only FLOPs incl. QK^T and PV
+D = 3072
+
+
+def dit_step_flops(l_img, l_txt):
+    L = l_img + l_txt
+    return 57 * (24 * L * D * D + 4 * L * L * D)
+
+
+F_VAE_1024 = 1.0472e13
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        j = json.loads(p.read_text())
+        return dict(tflops_sustained=j["bf16_tflops_sustained"], tflops_burst=j["bf16_tflops"], hbm=j["hbm_gbs"],
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(tflops_sustained=1400.0, tflops_burst=1590.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ----------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        # "under load": drop the idle tail by taking the median of the upper half
+        load = sm[len(sm) // 2:] if sm else []
+        med = load[len(load) // 2] if load else None
+        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port (CPU restatement of the reference) timed on host cores
+# ----------------------------------------------------------------------------------------------------------------------
+def cpu_reference_sample(repeats: int = 1) -> dict:
+    """One double-stream + one single-stream block at full width (L = 4096 + 512), f32 math on bf16-rounded tensors,
+    all host cores; extrapolated x19 / x38 x 50 steps (+ VAE by FLOPs) to images/s.  ~10-30 s of CPU work."""
+    import torch
+    from oracle import flux as OF
+    from oracle import ops as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = OF.FluxConfig(num_layers=1, num_single_layers=1, guidance_embeds=True)
+    w = OF.make_weights(cfg)
+    orc = OF.FluxOracle(cfg, w, O.REF)
+    l_img, l_txt = (HEIGHT // 16) * (WIDTH // 16), L_TXT
+    g = torch.Generator().manual_seed(1234)
+    img = O.rb(torch.randn(1, l_img, D, generator=g))
+    txt = O.rb(torch.randn(1, l_txt, D, generator=g))
+    vec = O.rb(torch.randn(1, D, generator=g))
+    pe = OF.embed_nd(OF.make_ids(HEIGHT // 16, WIDTH // 16, l_txt), O.REF)
+    best_d = best_s = float("inf")
+    for _ in range(max(1, repeats)):
+        t0 = time.perf_counter()
+        i2, t2 = orc.double_block(0, img, txt, vec, pe)
+        t1 = time.perf_counter()
+        x = orc.single_block(0, torch.cat([t2, i2], 1), vec, pe)
+        t2_ = time.perf_counter()
+        best_d, best_s = min(best_d, t1 - t0), min(best_s, t2_ - t1)
+    step_s = 19 * best_d + 38 * best_s
+    f_step = dit_step_flops(l_img, l_txt)
+    vae_s = step_s * F_VAE_1024 / f_step
+    img_s = NUM_STEPS * step_s + vae_s
+    return dict(value=1.0 / img_s, unit=UNIT, cores=cores, kind="port",
+                sample=(f"oracle port (torch CPU f32 on bf16-rounded tensors): 1 double block {best_d:.2f}s + 1 single "
+                        f"block {best_s:.2f}s at L=4608, extrapolated x19/x38 x{NUM_STEPS} steps + VAE by FLOPs"),
+                seconds_per_image=img_s, double_block_s=best_d, single_block_s=best_s)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    t0 = time.perf_counter()
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        cpu_reference_sample(1)
+    samples = [cpu_reference_sample(1) for _ in range(max(1, min(args.steps, 3)))]
+    best = max(samples, key=lambda s: s["value"])
+    line = {
+        "impl": "reference", "metric": METRIC, "value": best["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": best["seconds_per_image"] * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 math on bf16-rounded tensors",
+        "data": "synthetic",
+        "config": {"workload": "FLUX.1-dev 1024x1024 50-step batch=1 (reference CPU path, oracle port; the Rust "
+                               "reference cannot be built here: no cargo/rustc)", "l_img": 4096, "l_txt": L_TXT},
+        "cpu_baseline": {k: best[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": best["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200; there is no CPU fallback for the product path "
+                         "(use --impl reference for the CPU oracle port)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from diffusion_rs_b200 import build, lib as L
+    if rank == 0:
+        build.build()
+    if world > 1:
+        dist.barrier()
+    from diffusion_rs_b200.pipeline import (DiffusionGenerationParams, ModelSource, Pipeline, PromptEmbeds,
+                                            calculate_shift, latent_hw, make_ids, patchify)
+    lib = L.load()
+    quant = args.quant
+    t_load = time.perf_counter()
+    pipe = Pipeline.load(ModelSource.synthetic("black-forest-labs/FLUX.1-dev", quant=quant, num_layers=args.layers,
+                                               num_single_layers=args.single_layers))
+    torch.cuda.synchronize()
+    t_load = time.perf_counter() - t_load
+    params = DiffusionGenerationParams(height=args.height, width=args.width, num_steps=args.num_steps,
+                                       guidance_scale=GUIDANCE)
+    h, w = latent_hw(params.height, params.width)
+    h2, w2 = h // 2, w // 2
+    l_img, l_txt = h2 * w2, L_TXT
+    B = args.batch
+
+    # ---- synthetic prompt embeddings / noise: B images per rank (weak scaling); every rank builds the same global
+    #      prompt list, Pipeline.forward shards it by rank ----
+    all_prompts = [f"synthetic prompt {r}-{i}" for r in range(world) for i in range(B)]
+    all_embeds = [pipe.synthetic_embeds(p) for p in all_prompts]
+    all_noise = torch.randn(world * B, 16, h, w, generator=torch.Generator().manual_seed(1234)).to(torch.bfloat16)
+    embeds = all_embeds[rank * B:(rank + 1) * B]
+    noise = all_noise[rank * B:(rank + 1) * B]
+
+    # device-resident inputs for `value`
+    txt_d = torch.stack([e.txt for e in embeds]).cuda()
+    vec_d = torch.stack([e.vec for e in embeds]).cuda()
+    lat0 = patchify(noise).contiguous().cuda()
+    img_ids1, txt_ids1 = make_ids(h2, w2, l_txt)
+    img_ids = img_ids1[None].repeat(B, 1, 1).contiguous().cuda()
+    txt_ids = txt_ids1[None].repeat(B, 1, 1).contiguous().cuda()
+    sc = pipe.scheduler
+    mu = calculate_shift(l_img, sc.base_image_seq_len, sc.max_image_seq_len, sc.base_shift, sc.max_shift)
+    timesteps = sc.get_timesteps(params.num_steps, mu)
+    out_u8 = torch.empty(B, 16 * h2, 16 * w2, 3, dtype=torch.uint8, device="cuda")
+
+    def image_resident():
+        img = lat0.clone()
+        pipe.transformer.denoise(img, img_ids, txt_d, txt_ids, vec_d, GUIDANCE, timesteps)
+        pipe.vae.decode_packed_u8(img, h2, w2, out=out_u8)
+
+    def image_e2e():  # the public API call a user makes: host embeddings + host noise in, host u8 images out
+        return pipe.forward([PromptEmbeds(e.txt, e.vec) for e in all_embeds], params, noise=all_noise)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(k):
+            fn()
+        b.record()
+        barrier()
+        ms = a.elapsed_time(b)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
+    # ---- warm-up ----
+    for _ in range(args.warmup):
+        image_resident()
+    torch.cuda.synchronize()
+
+    # ---- timed: value (device-resident), with per-kernel-class event timing + launch counting + clocks ----
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    n0 = lib.fluxb200_launch_count(-1)
+    ms_total = timed(image_resident, args.steps)
+    launches = lib.fluxb200_launch_count(-1) - n0
+    # one more image with per-kernel-class CUDA events (two event records per launch) for the roofline numbers
+    nk = lib.fluxb200_profile_kinds()
+    kms, kfl, kby = (C.c_double * nk)(), (C.c_double * nk)(), (C.c_double * nk)()
+    kct = (C.c_uint64 * nk)()
+    kinds, ms_prof = {}, None
+    if args.kernel_timing:
+        lib.fluxb200_profile_enable(1)
+        ms_prof = timed(image_resident, 1)
+        lib.fluxb200_profile_enable(0)
+        L.check(lib.fluxb200_profile_collect(kms, kfl, kby, kct))
+        kinds = {lib.fluxb200_profile_kind_name(i).decode(): dict(ms=kms[i], flops=kfl[i], bytes=kby[i],
+                                                                    launches=int(kct[i])) for i in range(nk)}
+
+    # ---- timed: e2e through Pipeline.forward with host buffers ----
+    image_e2e()  # warm the pinned staging buffers
+    ms_e2e = timed(image_e2e, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    images = args.steps * B * world
+    value = images / (ms_total / 1e3)
+    e2e_value = images / (ms_e2e / 1e3)
+    pk = peaks()
+    f_img = params.num_steps * dit_step_flops(l_img, l_txt) * (args.layers or 19) / 19 + F_VAE_1024
+    gemm = kinds.get("gemm_tcgen05", {})
+    roofline = None
+    if gemm.get("launches"):
+        ach = gemm["flops"] / (gemm["ms"] / 1e3) / 1e12
+        traffic = None
+        tj = ROOT / "profiles" / "r1_gemm_traffic.json"
+        if tj.exists():
+            traffic = json.loads(tj.read_text()).get("dram_bytes_per_launch")
+        roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel", "achieved": ach,
+                    "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tflops_sustained"],
+                    "traffic": traffic, "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step)",
+                    "launches": gemm["launches"], "avg_launch_ms": gemm["ms"] / gemm["launches"],
+                    "share_of_step": gemm["ms"] / ms_prof}
+    cpu = cpu_reference_sample(1) if (world == 1 and not args.no_cpu_baseline) else None
+    h2d, d2h = pipe.io_bytes(B, params)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if quant is None else f"bf16 (weights {quant})", "data": "synthetic",
+        "config": {"workload": f"FLUX.1-dev {params.height}x{params.width} {params.num_steps}-step bf16 batch={B} per GPU "
+                               f"(1 step = 1 image = {params.num_steps} DiT steps + VAE decode)",
+                   "l_img": l_img, "l_txt": l_txt, "guidance": GUIDANCE, "weights": "random-init " + (quant or "bf16"),
+                   "parallelism": f"dp{world} (prompt sharding, NCCL weight broadcast at load only)",
+                   "l2": "inputs+weights per step (24 GB) >> 126 MB L2; no explicit flush needed",
+                   "double_layers": pipe.transformer.cfg.num_layers, "single_layers": pipe.transformer.cfg.num_single_layers},
+        "dit_ms_per_step": None, "images_per_s_per_gpu": value / world,
+        "frac_of_dense_gemm_roofline": (value / world) * f_img / (pk["tflops_sustained"] * 1e12),
+        "roofline": roofline, "kernels": kinds, "cpu_baseline": ({k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+                                                                 if cpu else None),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches), "clocks": clocks, "load_s": t_load,
+    }
+    line["dit_ms_per_step"] = (ms_total / args.steps) / params.num_steps  # upper bound: includes the VAE share
+    line["profiled_image_ms"] = ms_prof
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--quant", default=None, choices=[None, "nf4", "q4k"])
+    ap.add_argument("--height", type=int, default=HEIGHT)
+    ap.add_argument("--width", type=int, default=WIDTH)
+    ap.add_argument("--num-steps", type=int, default=NUM_STEPS, help="denoising steps per image")
+    ap.add_argument("--batch", type=int, default=1, help="images per GPU per step")
+    ap.add_argument("--layers", type=int, default=None, help="debug: reduced number of double blocks")
+    ap.add_argument("--single-layers", type=int, default=None, help="debug: reduced number of single blocks")
+    ap.add_argument("--no-kernel-timing", dest="kernel_timing", action="store_false")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -300,6 +300,8 @@ int launch_attention(const AttnDesc& d, cudaStream_t stream) {
   P.sl2 = d.scale * 1.4426950408889634f;
   P.out_a = d.out_a, P.out_b = d.out_b, P.ld_a = d.ld_a, P.ld_b = d.ld_b;
   const int grid = static_cast<int>(bh) * P.q_pairs;
+  ProfScope _ps(KK_ATTN, 4.0 * bh * static_cast<double>(d.L) * d.L * HD, 4.0 * bh * d.L * HD * 2.0, stream);
+  count_launch(KK_ATTN);
   attention_tcgen05_kernel<<<grid, ATT_THREADS, ATT_SMEM, stream>>>(P);
   FB_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -2,6 +2,7 @@
 #include <cudaTypedefs.h>
 
 #include <mutex>
+#include <vector>
 
 #include "internal.h"
 
@@ -14,6 +15,43 @@ const char* last_error() { return g_last_error.c_str(); }
 int fail(const std::string& msg) {
   g_last_error = msg;
   return -1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch accounting / profiling
+// ------------------------------------------------------------------------------------------------
+struct ProfRec {
+  cudaEvent_t a, b;
+  int kind;
+  double flops, bytes;
+};
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof_recs;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_pool;
+static unsigned long long g_launches[KK_COUNT] = {0};
+
+void count_launch(int kind, int n) { __atomic_fetch_add(&g_launches[kind], static_cast<unsigned long long>(n), __ATOMIC_RELAXED); }
+
+ProfScope::ProfScope(int k, double flops, double bytes, cudaStream_t st) : kind(k), stream(st), slot(-1) {
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ProfRec r;
+  if (!g_prof_pool.empty()) {
+    r.a = g_prof_pool.back().first, r.b = g_prof_pool.back().second;
+    g_prof_pool.pop_back();
+  } else {
+    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+  }
+  r.kind = k, r.flops = flops, r.bytes = bytes;
+  cudaEventRecord(r.a, st);
+  g_prof_recs.push_back(r);
+  slot = static_cast<int>(g_prof_recs.size()) - 1;
+}
+ProfScope::~ProfScope() {
+  if (slot < 0) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  cudaEventRecord(g_prof_recs[slot].b, stream);
 }
 
 int num_sms() {
@@ -97,3 +135,41 @@ int encode_tmap_4d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1,
 }
 
 }  // namespace fb
+
+// ---- C ABI: profiling / accounting ----
+extern "C" {
+void fluxb200_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(fb::g_prof_mu);
+  fb::g_prof_on = on != 0;
+}
+// Synchronises the device, folds every recorded event pair into per-kind totals and clears the records.
+// Arrays must hold fluxb200_profile_kinds() entries. ms = summed kernel time, count = event pairs.
+int fluxb200_profile_collect(double* ms, double* flops, double* bytes, unsigned long long* count) {
+  using namespace fb;
+  if (cudaDeviceSynchronize() != cudaSuccess) return fail("profile_collect: device synchronize failed");
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (int k = 0; k < KK_COUNT; ++k) ms[k] = flops[k] = bytes[k] = 0, count[k] = 0;
+  for (auto& r : g_prof_recs) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) {
+      ms[r.kind] += t, flops[r.kind] += r.flops, bytes[r.kind] += r.bytes, count[r.kind] += 1;
+    }
+    g_prof_pool.push_back({r.a, r.b});
+  }
+  g_prof_recs.clear();
+  return 0;
+}
+int fluxb200_profile_kinds(void) { return fb::KK_COUNT; }
+const char* fluxb200_profile_kind_name(int k) {
+  static const char* names[] = {"gemm_tcgen05", "attention_tcgen05", "ln_modulate", "qknorm_rope", "gemv_jobs",
+                                "dequant", "groupnorm", "misc"};
+  return (k >= 0 && k < fb::KK_COUNT) ? names[k] : "?";
+}
+// Kernel launches issued by this library since load (all kinds / one kind).
+unsigned long long fluxb200_launch_count(int kind) {
+  unsigned long long t = 0;
+  for (int k = 0; k < fb::KK_COUNT; ++k)
+    if (kind < 0 || kind == k) t += __atomic_load_n(&fb::g_launches[k], __ATOMIC_RELAXED);
+  return t;
+}
+}

@@ -82,6 +82,8 @@ int launch_ln_modulate(const bf16* x, long long in_bstride_rows, int in_row_off,
                        cudaStream_t stream) {
   FB_REQUIRE(D == 3072, "ln_modulate: hidden size must be 3072 (HIDDEN_SIZE, model.rs:17)");
   const int total = rows_per_batch * batch;
+  ProfScope _ps(KK_LN_MOD, 0, 4.0 * total * D, stream);
+  count_launch(KK_LN_MOD, 1);
   ln_modulate_kernel<3072><<<(total + 3) / 4, 128, 0, stream>>>(x, in_bstride_rows, in_row_off, rows_per_batch, total,
                                                                 shift, scale, mod_bstride, out, eps);
   FB_CHECK_CUDA(cudaGetLastError());
@@ -151,6 +153,8 @@ int launch_qknorm_rope(const bf16* qkv, long long ld, int rows_per_batch, int ba
                        const bf16* wq, const bf16* wk, const bf16* pe_cos, const bf16* pe_sin, long long pe_bstride,
                        bf16* Q, bf16* K, bf16* V, float eps, cudaStream_t stream) {
   const int rows = rows_per_batch * batch;
+  ProfScope _ps(KK_QKNORM_ROPE, 0, 12.0 * rows * H * 128, stream);
+  count_launch(KK_QKNORM_ROPE, 1);
   qknorm_rope_kernel<<<rows, 256, 0, stream>>>(qkv, ld, rows_per_batch, H, L, l_off, wq, wk, pe_cos, pe_sin,
                                                pe_bstride, Q, K, V, eps);
   FB_CHECK_CUDA(cudaGetLastError());
@@ -232,6 +236,8 @@ int launch_gemv_jobs(const GemvJob* jobs_dev, int njobs, int row_base, int total
   const size_t smem = static_cast<size_t>(B) * K * 2;
   FB_REQUIRE(smem <= 96 * 1024, "gemv_jobs: batch*K too large for shared memory");
   const int grid = (total_rows + 31) / 32;
+  ProfScope _ps(KK_GEMV, 2.0 * total_rows * K * B, 2.0 * total_rows * K, stream);
+  count_launch(KK_GEMV);
   if (B <= 2) {
     static bool set2 = false;
     if (!set2) {
@@ -264,6 +270,7 @@ __global__ void silu_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, lo
   y[i] = __float2bfloat16_rn(v / d);
 }
 int launch_silu(const bf16* x, bf16* y, long long n, cudaStream_t stream) {
+  count_launch(KK_MISC);
   silu_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(x, y, n);
   FB_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -284,6 +291,7 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ t, bf16* __r
 }
 int launch_timestep_embedding(const float* t, bf16* out, int B, int dim, cudaStream_t stream) {
   const int n = B * dim / 2;
+  count_launch(KK_MISC);
   timestep_embedding_kernel<<<(n + 127) / 128, 128, 0, stream>>>(t, out, B, dim);
   FB_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -300,6 +308,7 @@ __global__ void vec_combine_kernel(const bf16* __restrict__ a, const bf16* __res
   out[i] = __float2bfloat16_rn(v);
 }
 int launch_vec_combine(const bf16* a, const bf16* g, const bf16* y, bf16* out, int n, cudaStream_t stream) {
+  count_launch(KK_MISC);
   vec_combine_kernel<<<(n + 255) / 256, 256, 0, stream>>>(a, g, y, out, n);
   FB_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -314,6 +323,7 @@ __global__ void euler_kernel(bf16* __restrict__ img, const bf16* __restrict__ pr
 }
 int launch_euler(bf16* img, const bf16* pred, float dt, long long n, cudaStream_t stream) {
   const float dtb = __bfloat162float(__float2bfloat16_rn(dt));
+  count_launch(KK_MISC);
   euler_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(img, pred, dtb, n);
   FB_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -328,6 +338,7 @@ __global__ void affine_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, 
 int launch_affine(const bf16* x, bf16* y, float mul, float add, long long n, cudaStream_t stream) {
   const float mb = __bfloat162float(__float2bfloat16_rn(mul));
   const float ab = __bfloat162float(__float2bfloat16_rn(add));
+  count_launch(KK_MISC);
   affine_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(x, y, mb, ab, n);
   FB_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -609,6 +609,7 @@ static int prepare_invariants(fluxb200_model* m, const Workspace& w, const StepI
   const int L = l_img + l_txt;
   {
     const int n1 = B * l_txt * 64, n2 = B * l_img * 64;
+    count_launch(KK_MISC, 2);
     pe_table_kernel<<<(n1 + 255) / 256, 256, 0, st>>>(io.txt_ids, l_txt, B, L, 0, w.pe_cos, w.pe_sin);
     pe_table_kernel<<<(n2 + 255) / 256, 256, 0, st>>>(io.img_ids, l_img, B, L, l_txt, w.pe_cos, w.pe_sin);
     FB_CHECK_CUDA(cudaGetLastError());

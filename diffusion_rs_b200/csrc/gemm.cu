@@ -396,6 +396,14 @@ int launch_gemm(const GemmDesc* descs, int count, cudaStream_t stream) {
     p.alpha = d.alpha, p.has_alpha = (d.alpha != 1.0f);
   }
   P.total_tiles = tile;
+  double flops = 0, bytes = 0;
+  for (int i = 0; i < count; ++i) {
+    flops += 2.0 * descs[i].M * static_cast<double>(descs[i].N) * descs[i].K;
+    bytes += 2.0 * (static_cast<double>(descs[i].M) * descs[i].K + static_cast<double>(descs[i].N) * descs[i].K +
+                    static_cast<double>(descs[i].M) * descs[i].N);
+  }
+  ProfScope _ps(KK_GEMM, flops, bytes, stream);
+  count_launch(KK_GEMM);
   int grid = std::min(tile, num_sms());
   gemm_tcgen05_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(P);
   FB_CHECK_CUDA(cudaGetLastError());

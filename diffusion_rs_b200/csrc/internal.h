@@ -41,6 +41,17 @@ int encode_tmap_4d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1,
 
 int num_sms();
 
+// ---- launch accounting + optional per-kernel-class CUDA-event timing (bench.py roofline evidence) ----
+enum KernelKind { KK_GEMM = 0, KK_ATTN, KK_LN_MOD, KK_QKNORM_ROPE, KK_GEMV, KK_DEQUANT, KK_GROUPNORM, KK_MISC, KK_COUNT };
+void count_launch(int kind, int n = 1);
+struct ProfScope {  // records an event pair around the launches issued in its lifetime when profiling is enabled
+  ProfScope(int kind, double flops, double bytes, cudaStream_t stream);
+  ~ProfScope();
+  int kind;
+  cudaStream_t stream;
+  int slot;
+};
+
 // ---- tcgen05 GEMM  out[M,N] = epilogue(A[M,K] . W[N,K]^T) ----
 enum { ACT_NONE = 0, ACT_GELU = 1 };
 enum { BIAS_NONE = 0, BIAS_FUSED = 1, BIAS_AFTER_ROUND = 2 };

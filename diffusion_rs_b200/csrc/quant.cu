@@ -138,6 +138,8 @@ int launch_dequant_bnb4(const uint8_t* packed, const float* absmax, bf16* out, i
   FB_REQUIRE(blocksize >= 2 && blocksize % 2 == 0, "dequant_bnb4: bad blocksize");
   const long long nbytes = (n + 1) / 2;
   const unsigned grid = static_cast<unsigned>((nbytes + 16 * 256 - 1) / (16 * 256));
+  ProfScope _ps(KK_DEQUANT, 0, 2.5 * n, stream);
+  count_launch(KK_DEQUANT);
   if (is_nf4)
     dequant_4bit_kernel<bf16, 2><<<grid, 256, 0, stream>>>(packed, absmax, out, blocksize / 2, n);
   else
@@ -148,6 +150,7 @@ int launch_dequant_bnb4(const uint8_t* packed, const float* absmax, bf16* out, i
 
 int launch_dequant_int8(const int8_t* w, const float* scb, bf16* out, int col, long long n, cudaStream_t stream) {
   const unsigned grid = static_cast<unsigned>((n + 16 * 256 - 1) / (16 * 256));
+  count_launch(KK_DEQUANT);
   dequant_int8_rowwise_kernel<bf16><<<grid, 256, 0, stream>>>(w, scb, out, col, n);
   FB_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -206,6 +209,8 @@ __global__ void __launch_bounds__(256) dequant_q4k_kernel(const uint8_t* __restr
 int launch_dequant_q4k(const uint8_t* blocks, bf16* out, long long n, cudaStream_t stream) {
   FB_REQUIRE(n % 256 == 0, "dequant_q4k: element count must be a multiple of 256");
   const long long nblocks = n / 256;
+  ProfScope _ps(KK_DEQUANT, 0, 2.5625 * n, stream);
+  count_launch(KK_DEQUANT);
   dequant_q4k_kernel<<<static_cast<unsigned>((nblocks + 7) / 8), 256, 0, stream>>>(blocks, out, nblocks);
   FB_CHECK_CUDA(cudaGetLastError());
   return 0;

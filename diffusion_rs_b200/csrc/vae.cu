@@ -27,14 +27,14 @@ __device__ __forceinline__ float silu_steps(float v) {  // core/op.rs:703-705, b
 template <int PASS>
 __global__ void __launch_bounds__(256) gn_stats_kernel(const bf16* __restrict__ x, double* __restrict__ stats, int HW,
                                                        int C, int groups, int pix_per_block) {
-  __shared__ float part[64];
+  __shared__ double part[64];  // f64 partials: the result does not depend on the (unordered) atomic arrival order
   const int n = blockIdx.y;
   const int cv = C / 8;                 // vectors per pixel
   const int rows = blockDim.x / cv;     // pixels processed per iteration
   const int vec = threadIdx.x % cv;
   const int prow = threadIdx.x / cv;
   const int cpg = C / groups;
-  if (threadIdx.x < 64) part[threadIdx.x] = 0.f;
+  if (threadIdx.x < 64) part[threadIdx.x] = 0.0;
   __syncthreads();
   float mean0 = 0.f, mean1 = 0.f;
   const int g0 = (vec * 8) / cpg;
@@ -64,12 +64,12 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const bf16* __restrict__ 
       }
     }
   }
-  atomicAdd(&part[g0], a0);
-  atomicAdd(&part[g1], a1);
+  atomicAdd(&part[g0], static_cast<double>(a0));
+  atomicAdd(&part[g1], static_cast<double>(a1));
   __syncthreads();
   if (threadIdx.x < groups) {
-    const float v = part[threadIdx.x];
-    if (v != 0.f) atomicAdd(&stats[(n * groups + threadIdx.x) * 2 + PASS], static_cast<double>(v));
+    const double v = part[threadIdx.x];
+    if (v != 0.0) atomicAdd(&stats[(n * groups + threadIdx.x) * 2 + PASS], v);
   }
 }
 
@@ -111,6 +111,8 @@ int launch_groupnorm_silu(const bf16* x, const bf16* w, const bf16* b, bf16* y, 
              "groupnorm: needs 32 groups, >= 4 channels per group and C/8 dividing 256");
   FB_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * N * groups * 2, stream));
   const int pix_per_block = 1024;
+  ProfScope _ps(KK_GROUPNORM, 0, 8.0 * N * HW * C, stream);
+  count_launch(KK_GROUPNORM, 3);
   dim3 grid((HW + pix_per_block - 1) / pix_per_block, N);
   gn_stats_kernel<0><<<grid, 256, 0, stream>>>(x, stats, HW, C, groups, pix_per_block);
   gn_stats_kernel<1><<<grid, 256, 0, stream>>>(x, stats, HW, C, groups, pix_per_block);
@@ -138,6 +140,7 @@ __global__ void upsample2x_kernel(const bf16* __restrict__ x, bf16* __restrict__
 }
 int launch_upsample2x_nhwc(const bf16* x, bf16* y, int N, int H, int W, int C, cudaStream_t stream) {
   const long long total_vec = static_cast<long long>(N) * 4 * H * W * (C / 8);
+  count_launch(KK_MISC);
   upsample2x_kernel<<<static_cast<unsigned>((total_vec + 255) / 256), 256, 0, stream>>>(x, y, H, W, C, total_vec);
   FB_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -196,6 +199,7 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(bf16* __restrict__ x,
 }
 int launch_softmax_rows_bf16(bf16* x, long long rows, int cols, cudaStream_t stream) {
   FB_REQUIRE(cols % 8 == 0, "softmax_rows: cols must be a multiple of 8");
+  count_launch(KK_MISC);
   softmax_rows_kernel<<<static_cast<unsigned>(rows), 256, 0, stream>>>(x, cols);
   FB_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -219,6 +223,7 @@ __global__ void transpose_kernel(const bf16* __restrict__ x, bf16* __restrict__ 
 }
 static int launch_transpose_batched(const bf16* x, bf16* y, int batch, int rows, int cols, cudaStream_t stream) {
   dim3 grid((cols + 31) / 32, (rows + 31) / 32, batch);
+  count_launch(KK_MISC);
   transpose_kernel<<<grid, dim3(32, 8), 0, stream>>>(x, y, rows, cols);
   FB_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -246,6 +251,7 @@ __global__ void repack_conv_weight_kernel(const bf16* __restrict__ w, bf16* __re
 }
 int launch_repack_conv_weight(const bf16* w, bf16* out, int Cout, int Cin, int taps, cudaStream_t stream) {
   const long long total = static_cast<long long>(Cout) * Cin * taps;
+  count_launch(KK_MISC);
   repack_conv_weight_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(w, out, Cin, taps, total);
   FB_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -273,6 +279,7 @@ int launch_unpack_latents(const bf16* packed, bf16* nhwc, int N, int h2, int w2,
   const long long total = static_cast<long long>(N) * 4 * h2 * w2 * 16;
   const float isb = __bfloat162float(__float2bfloat16_rn(inv_scale));
   const float shb = __bfloat162float(__float2bfloat16_rn(shift));
+  count_launch(KK_MISC);
   unpack_latents_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(packed, nhwc, h2, w2, isb, shb,
                                                                                         total);
   FB_CHECK_CUDA(cudaGetLastError());
@@ -302,6 +309,7 @@ __global__ void postprocess_u8_kernel(const bf16* __restrict__ x, uint8_t* __res
 int launch_postprocess_u8(const bf16* nhwc, uint8_t* out, int N, int C, int H, int W, int to_nchw,
                           cudaStream_t stream) {
   const long long total = static_cast<long long>(N) * H * W * C;
+  count_launch(KK_MISC);
   postprocess_u8_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
       nhwc, out, C, static_cast<long long>(H) * W, to_nchw, total);
   FB_CHECK_CUDA(cudaGetLastError());

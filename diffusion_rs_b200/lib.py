@@ -61,6 +61,12 @@ SIGNATURES = {
                                               C.c_uint64, c_void_p]),
     "fluxb200_conv2d_nhwc": (c_int, [c_void_p] * 5 + [c_int] * 6 + [c_void_p]),
     "fluxb200_repack_conv_weight": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "fluxb200_profile_enable": (None, [c_int]),
+    "fluxb200_profile_kinds": (c_int, []),
+    "fluxb200_profile_kind_name": (C.c_char_p, [c_int]),
+    "fluxb200_profile_collect": (c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                         C.POINTER(C.c_uint64)]),
+    "fluxb200_launch_count": (C.c_uint64, [c_int]),
     "fluxb200_groupnorm_nhwc": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_float, c_int, c_void_p, c_void_p]),
 }
 

@@ -199,6 +199,19 @@ int fluxb200_groupnorm_nhwc(const void* x, const void* weight, const void* bias,
                             int32_t C, int32_t groups, float eps, int32_t silu, void* stats_scratch,
                             fluxb200_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Launch accounting and optional per-kernel-class CUDA-event timing (evidence for bench.py; the reference has
+ * only tracing spans, models/flux/model.rs:240-453).  Timing is off by default and costs two event records per
+ * launch when enabled.
+ * ---------------------------------------------------------------------------------------------- */
+void fluxb200_profile_enable(int on);
+int fluxb200_profile_kinds(void);
+const char* fluxb200_profile_kind_name(int kind);
+/* Synchronises the device; ms/flops/bytes/count must each hold fluxb200_profile_kinds() entries. */
+int fluxb200_profile_collect(double* ms, double* flops, double* bytes, unsigned long long* count);
+/* Kernel launches issued by the library since load; kind < 0 => all kinds. */
+unsigned long long fluxb200_launch_count(int kind);
+
 #ifdef __cplusplus
 }
 #endif

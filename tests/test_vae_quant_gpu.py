@@ -36,7 +36,8 @@ def test_conv2d_nhwc(fluxlib, N, H, W, Cin, Cout, k):
     L.check(fluxlib.fluxb200_repack_conv_weight(wd.data_ptr(), wp.data_ptr(), Cout, Cin, k, L.current_stream()))
     assert torch.equal(wp.cpu(), w.permute(0, 2, 3, 1).contiguous())
     out = torch.empty(N, H, W, Cout, device="cuda", dtype=torch.bfloat16)
-    L.check(fluxlib.fluxb200_conv2d_nhwc(xd.data_ptr(), wp.data_ptr(), b.cuda().data_ptr(), None, out.data_ptr(), N, H,
+    bd = b.cuda()
+    L.check(fluxlib.fluxb200_conv2d_nhwc(xd.data_ptr(), wp.data_ptr(), bd.data_ptr(), None, out.data_ptr(), N, H,
                                          W, Cin, Cout, k, L.current_stream()))
     got = out.permute(0, 3, 1, 2).float().cpu()
     assert _rel(got, ref) < 2e-3
@@ -56,7 +57,8 @@ def test_groupnorm_nhwc(fluxlib, N, HW, C, silu):
     xd = x.permute(0, 2, 1).contiguous().cuda()
     out = torch.empty_like(xd)
     stats = torch.zeros(N * 64, dtype=torch.float64, device="cuda")
-    L.check(fluxlib.fluxb200_groupnorm_nhwc(xd.data_ptr(), w.cuda().data_ptr(), b.cuda().data_ptr(), out.data_ptr(), N,
+    wd, bd = w.cuda(), b.cuda()  # keep the device copies alive across the call
+    L.check(fluxlib.fluxb200_groupnorm_nhwc(xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), out.data_ptr(), N,
                                             HW, C, 32, 1e-6, silu, stats.data_ptr(), L.current_stream()))
     got = out.permute(0, 2, 1).float().cpu()
     assert (got != ref).float().mean().item() < 5e-3
@@ -117,8 +119,8 @@ def test_bnb_4bit_ffi_symbols(fluxlib, kind, ty):
     out = torch.empty(n, dtype=tdt, device="cuda")
     code = torch.zeros(16, dtype=torch.float32, device="cuda")
     fn = getattr(fluxlib, f"dequantize_blockwise_{ty}_{kind}")
-    fn(code.data_ptr(), torch.from_numpy(packed).cuda().data_ptr(), torch.from_numpy(absmax).cuda().data_ptr(),
-       out.data_ptr(), bs, n, L.current_stream())
+    pd, ad = torch.from_numpy(packed).cuda(), torch.from_numpy(absmax).cuda()
+    fn(code.data_ptr(), pd.data_ptr(), ad.data_ptr(), out.data_ptr(), bs, n, L.current_stream())
     torch.cuda.synchronize()
     assert torch.equal(out.cpu(), torch.from_numpy(ref).to(tdt))
 
@@ -133,8 +135,8 @@ def test_bnb_int8_ffi_symbols(fluxlib):
     absmax = np.abs(rs.randn((n + bs - 1) // bs)).astype(np.float32)
     ref = Q.dequant_blockwise_int8(code, q, absmax, bs)
     out = torch.empty(n, dtype=torch.float32, device="cuda")
-    fluxlib.dequantize_blockwise_f32_int8(torch.from_numpy(code).cuda().data_ptr(), torch.from_numpy(q).cuda().data_ptr(),
-                                          torch.from_numpy(absmax).cuda().data_ptr(), out.data_ptr(), bs, n,
+    cd, qd, ad = torch.from_numpy(code).cuda(), torch.from_numpy(q).cuda(), torch.from_numpy(absmax).cuda()
+    fluxlib.dequantize_blockwise_f32_int8(cd.data_ptr(), qd.data_ptr(), ad.data_ptr(), out.data_ptr(), bs, n,
                                           L.current_stream())
     torch.cuda.synchronize()
     assert torch.equal(out.cpu(), torch.from_numpy(ref))
@@ -145,8 +147,9 @@ def test_bnb_int8_ffi_symbols(fluxlib):
     ref = Q.dequant_int8_rowwise(w8, scb)
     out = torch.empty(rows, cols, dtype=torch.bfloat16, device="cuda")
     torch.cuda.synchronize()
-    fluxlib.dequantize_8bit_kernel_bf16(torch.from_numpy(w8).cuda().data_ptr(), torch.from_numpy(scb).cuda().data_ptr(),
-                                        out.data_ptr(), rows, cols, rows * cols)
+    wd, sd = torch.from_numpy(w8).cuda(), torch.from_numpy(scb).cuda()
+    torch.cuda.synchronize()
+    fluxlib.dequantize_8bit_kernel_bf16(wd.data_ptr(), sd.data_ptr(), out.data_ptr(), rows, cols, rows * cols)
     torch.cuda.synchronize()
     assert torch.equal(out.cpu(), torch.from_numpy(ref).bfloat16())
 
@@ -158,8 +161,8 @@ def test_q4k_dequant(fluxlib):
     blocks = Q.quantize_q4k(w)
     ref = Q.dequant_q4k_bf16(blocks).reshape(64, 1024)
     out = torch.empty(64, 1024, dtype=torch.bfloat16, device="cuda")
-    L.check(fluxlib.fluxb200_dequantize_q4k_bf16(torch.from_numpy(blocks).cuda().data_ptr(), out.data_ptr(), 64 * 1024,
-                                                 L.current_stream()))
+    bd = torch.from_numpy(blocks).cuda()
+    L.check(fluxlib.fluxb200_dequantize_q4k_bf16(bd.data_ptr(), out.data_ptr(), 64 * 1024, L.current_stream()))
     torch.cuda.synchronize()
     assert torch.equal(out.float().cpu(), torch.from_numpy(ref))
 
