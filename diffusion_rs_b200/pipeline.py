@@ -127,6 +127,27 @@ def make_ids(h2: int, w2: int, l_txt: int, dtype=torch.bfloat16):  # State::new 
     return img_ids.reshape(h2 * w2, 3).to(dtype), torch.zeros(l_txt, 3, dtype=dtype)
 
 
+def shard_range(n: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous slice of the prompt batch owned by `rank` (prompts [0..N) -> N/world per rank)."""
+    per = (n + world - 1) // world
+    return min(n, rank * per), min(n, (rank + 1) * per)
+
+
+def dist_info():
+    d = torch.distributed
+    if d.is_available() and d.is_initialized():
+        return d, d.get_rank(), d.get_world_size()
+    return None, 0, 1
+
+
+def broadcast_weight(t: torch.Tensor) -> torch.Tensor:
+    """The only collective on the path: rank 0's weights are broadcast once at load (NCCL on GPUs, gloo in tests)."""
+    d, _, world = dist_info()
+    if world > 1:
+        d.broadcast(t, src=0)
+    return t
+
+
 NOISE_SEED = 299792458  # the reference seeds cuRAND with this constant (cuda_backend/device.rs:206)
 
 
@@ -161,14 +182,7 @@ class Pipeline:
             fcfg.num_single_layers = source.num_single_layers
         vcfg = VaeConfig()
         sched = SchedulerConfig(use_dynamic_shifting=is_dev, shift=3.0 if is_dev else 1.0)
-        dist = torch.distributed if (torch.distributed.is_available() and torch.distributed.is_initialized()) else None
-        rank = dist.get_rank() if dist else 0
-        world = dist.get_world_size() if dist else 1
-
-        def bcast(t):  # NCCL broadcast of weights at load only (north_star / SURVEY §8(e))
-            if world > 1:
-                dist.broadcast(t, src=0)
-            return t
+        bcast = broadcast_weight  # NCCL broadcast of weights at load only (north_star / SURVEY §8(e))
 
         tr = FluxTransformer(fcfg)
         va = AutoEncoderKl(vcfg)
@@ -224,11 +238,8 @@ class Pipeline:
             noise = torch.randn(n, 16, h, w, generator=torch.Generator().manual_seed(seed), dtype=torch.float32)
         noise = noise.to(torch.bfloat16)
         # shard the prompt batch over ranks (contiguous slices); every rank returns only its own images
-        dist = torch.distributed if (torch.distributed.is_available() and torch.distributed.is_initialized()) else None
-        rank = dist.get_rank() if dist else 0
-        world = dist.get_world_size() if dist else 1
-        per = (n + world - 1) // world
-        lo, hi = min(n, rank * per), min(n, (rank + 1) * per)
+        _, rank, world = dist_info()
+        lo, hi = shard_range(n, rank, world)
         images = []
         for s in range(lo, hi, self.max_batch):
             e = min(hi, s + self.max_batch)

@@ -162,3 +162,89 @@ def quantize_q4k(w: np.ndarray) -> np.ndarray:
     for g in range(4):
         out[:, 16 + g * 32:16 + (g + 1) * 32] = q[:, 2 * g] | (q[:, 2 * g + 1] << 4)
     return out.reshape(*w.shape[:-1], w.shape[-1] // QK_K, Q4K_BYTES)
+
+
+# ---- the reference's own Q4_K quantiser, restated so that its round-trip KAT can pin this file ---------------
+def _nearest_int(v) -> int:
+    """quantized/utils.rs:3-5 — f32::round: half away from zero."""
+    v = float(v)
+    import math
+    return int(math.floor(abs(v) + 0.5)) * (1 if v >= 0 else -1)
+
+
+def make_qkx1_quants(nmax: int, ntry: int, x: np.ndarray):
+    """quantized/utils.rs:227-284 (sequential f32 arithmetic)."""
+    f = np.float32
+    x = x.astype(np.float32)
+    n = x.size
+    l = [0] * n
+    mn, mx = f(x.min()), f(x.max())
+    if mx == mn:
+        return f(0.0), f(0.0)
+    mn = f(min(mn, f(0.0)))
+    iscale = f(f(nmax) / f(mx - mn))
+    scale = f(f(1.0) / iscale)
+    for _ in range(ntry):
+        sumlx, suml2, did_change = f(0.0), 0, False
+        for i in range(n):
+            li = max(0, min(nmax, _nearest_int(f(iscale * f(x[i] - mn)))))
+            if li != l[i]:
+                l[i] = li
+                did_change = True
+            sumlx = f(sumlx + f(f(x[i] - mn) * f(li)))
+            suml2 += li * li
+        scale = f(sumlx / f(suml2))
+        s = f(0.0)
+        for i in range(n):
+            s = f(s + f(x[i] - f(scale * f(l[i]))))
+        mn = f(s / f(n))
+        if mn > 0:
+            mn = f(0.0)
+        iscale = f(f(1.0) / scale)
+        if not did_change:
+            break
+    return scale, f(-mn)
+
+
+def quantize_q4k_reference(xs: np.ndarray) -> np.ndarray:
+    """BlockQ4K::from_float (k_quants.rs:1432-1494). xs: f32 [n], n % 256 == 0 -> u8 [n/256, 144]."""
+    f = np.float32
+    xs = np.ascontiguousarray(xs, dtype=np.float32).reshape(-1, QK_K)
+    out = np.zeros((xs.shape[0], Q4K_BYTES), dtype=np.uint8)
+    for b, x in enumerate(xs):
+        scales, mins = [], []
+        for j in range(8):
+            s, m = make_qkx1_quants(15, 5, x[32 * j:32 * j + 32])
+            scales.append(s)
+            mins.append(m)
+        max_scale = f(max([f(0.0)] + scales))
+        max_min = f(max([f(0.0)] + mins))
+        inv_scale = f(f(63.0) / max_scale) if max_scale > 0 else f(0.0)
+        inv_min = f(f(63.0) / max_min) if max_min > 0 else f(0.0)
+        sc = np.zeros(12, dtype=np.uint8)
+        for j in range(8):
+            ls = min(_nearest_int(f(inv_scale * scales[j])), 63)
+            lm = min(_nearest_int(f(inv_min * mins[j])), 63)
+            if j < 4:
+                sc[j] = ls
+                sc[j + 4] = lm
+            else:
+                sc[j + 4] = (ls & 0xF) | ((lm & 0xF) << 4)
+                sc[j - 4] |= (ls >> 4) << 6
+                sc[j] |= (lm >> 4) << 6
+        d16 = np.float16(f(max_scale / f(63.0)))
+        m16 = np.float16(f(max_min / f(63.0)))
+        out[b, 0:2] = np.frombuffer(d16.tobytes(), dtype=np.uint8)
+        out[b, 2:4] = np.frombuffer(m16.tobytes(), dtype=np.uint8)
+        out[b, 4:16] = sc
+        l = np.zeros(QK_K, dtype=np.uint8)
+        for j in range(8):
+            s6, m6 = get_scale_min_k4(j, sc)
+            d = f(f(d16) * f(int(s6)))
+            if d != 0:
+                dm = f(f(m16) * f(int(m6)))
+                for ii in range(32):
+                    l[32 * j + ii] = max(0, min(15, _nearest_int(f(f(x[32 * j + ii] + dm) / d))))
+        for g in range(4):
+            out[b, 16 + g * 32:16 + (g + 1) * 32] = l[g * 64:g * 64 + 32] | (l[g * 64 + 32:g * 64 + 64] << 4)
+    return out
