@@ -6,10 +6,11 @@
 // (diffusion_rs_backend/src/unquantized/mod.rs:34-77, cublaslt/matmul.rs:502-586) and, in conv mode,
 // the im2col + GEMM + NHWC->NCHW copy of diffusion_rs_common/src/core/cuda_backend/mod.rs:1545-1599.
 //
-// Structure (one CTA per SM, 192 threads):
+// Structure (one CTA per SM, 320 threads):
 //   warp 0      TMA producer   : 4-stage ring of {A 128x64, W 256x64} bf16 tiles, 128B swizzle
 //   warp 1      MMA issuer     : tcgen05.mma cta_group::1 kind::f16, M=128 N=256 K=16, accumulators in TMEM
-//   warps 2..5  epilogue       : tcgen05.ld -> fused bias / GELU / alpha / gate*x+residual -> bf16 global stores
+//   warps 2..9  epilogue       : tcgen05.ld -> fused bias / GELU / alpha / gate*x+residual in packed bf16x2 math
+//                                (compile-time variants, no per-element branches) -> bf16 global stores
 // TMEM holds two 128x256 fp32 accumulators so the epilogue of tile i overlaps the mainloop of tile i+1.
 // A launch may carry up to 4 problems (grouped GEMM) so the 512-token text stream shares a wave with the
 // 4096-token image stream instead of leaving 2/3 of the SMs idle.
@@ -27,7 +28,8 @@ static constexpr int STAGES = 4;
 static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
 static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;  // 32 KB
 static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-static constexpr int GEMM_THREADS = 192;
+static constexpr int GEMM_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+static constexpr int EPI_WARPS = 8;
 static constexpr int MAX_PROBLEMS = 4;
 static constexpr int GROUP_M = 8;
 static constexpr int CONV_TH = 8, CONV_TW = 16;  // 8x16 output pixels = one 128-row M tile
@@ -42,7 +44,7 @@ struct alignas(64) GemmProblemDev {
   bf16* out0;
   bf16* out1;
   long long ld0, ld1;
-  int n_split, col_off1, act0, act1;
+  int n_split, col_off1, ev0, ev1;  // EV_* epilogue variant of each output segment
   const bf16* bias;
   const bf16* gate;
   const bf16* res;
@@ -57,18 +59,103 @@ struct GemmParams {
   int total_tiles;
 };
 
+// ------------------------------------------------------------------------------------------------
+// Epilogue math.  The reference rounds to bf16 after every tensor op; a bf16 HW multiply / add (HMUL2.BF16 /
+// HADD2.BF16) is exactly "f32 op, then round-to-nearest-even to bf16" for bf16 inputs (products of two 8-bit
+// mantissas are exact in f32; sums are exact in f32 whenever the smaller addend can matter), so the chain runs on
+// packed bf16x2 registers with no conversions.
+// ------------------------------------------------------------------------------------------------
+typedef __nv_bfloat162 bf162;
+__device__ __forceinline__ bf162 as_bf162(uint32_t u) { return *reinterpret_cast<bf162*>(&u); }
+__device__ __forceinline__ uint32_t as_u32(bf162 v) { return *reinterpret_cast<uint32_t*>(&v); }
+__device__ __forceinline__ bf162 bf162_const(float x) { return __float2bfloat162_rn(x); }
+
+// tanh accurate to a few f32 ulps (far below bf16 resolution): 1 - 2/(exp(2|x|)+1), cubic near 0
+__device__ __forceinline__ float tanh_f32(float x) {
+  const float ax = fabsf(x);
+  const float e = exp2f(ax * 2.8853900817779268f);
+  float r = 1.0f - __fdividef(2.0f, e + 1.0f);
+  const float x2 = ax * ax;
+  const float small = ax * (1.0f - x2 * (0.3333333433f - 0.13333334f * x2));
+  r = ax < 0.03125f ? small : r;
+  return copysignf(r, x);
+}
+
 // tanh-GELU with the reference's bf16 op-by-op rounding (diffusion_rs_common/src/core/op.rs:539-578):
 //   0.5*v*(1 + tanh(c*v*(1 + 0.044715*v*v)))   evaluated left to right, every product/sum rounded to bf16.
+__device__ __forceinline__ bf162 gelu_bf16x2(bf162 v) {
+  const bf162 kHalf = bf162_const(0.5f), kOne = bf162_const(1.0f);
+  const bf162 kC = bf162_const(0.79788456080286535587989211986876373f), kK = bf162_const(0.044715f);
+  const bf162 a = __hmul2(kHalf, v);
+  const bf162 p = __hadd2(kOne, __hmul2(__hmul2(kK, v), v));
+  const bf162 q = __hmul2(__hmul2(kC, v), p);
+  const float2 qf = __bfloat1622float2(q);
+  const bf162 t = __floats2bfloat162_rn(tanh_f32(qf.x), tanh_f32(qf.y));
+  return __hmul2(a, __hadd2(kOne, t));
+}
+// scalar (slow-path) version, same arithmetic
 __device__ __forceinline__ float gelu_bf16_steps(float v) {
-  const float kHalf = 0.5f;
-  const float kC = __bfloat162float(__float2bfloat16_rn(0.79788456080286535587989211986876373f));
-  const float kK = __bfloat162float(__float2bfloat16_rn(0.044715f));
-  float a = rbf(kHalf * v);
-  float p = rbf(1.0f + rbf(rbf(kK * v) * v));
-  float q = rbf(rbf(kC * v) * p);
-  float t = rbf(tanhf(q));
-  float s = rbf(1.0f + t);
-  return rbf(a * s);
+  const bf162 r = gelu_bf16x2(__floats2bfloat162_rn(v, v));
+  return __low2float(r);
+}
+
+enum { EV_PLAIN = 0, EV_GELU = 1, EV_RES = 2, EV_GATE_RES = 3, EV_ALPHA = 4, EV_KINDS = 5 };  // x bias mode (3)
+
+// 16 consecutive output columns of one row: acc (fp32, from TMEM) -> bf16, fully unrolled, compile-time variant.
+template <int BIAS, int EV>
+__device__ __forceinline__ void epi16(const uint32_t* acc, bf16* outp, const bf16* biasp, const bf16* gatep,
+                                      const bf16* resp, bf162 alpha2) {
+  uint32_t b[8], g[8], r[8], o[8];
+  if (BIAS != BIAS_NONE) {
+    *reinterpret_cast<uint4*>(&b[0]) = *reinterpret_cast<const uint4*>(biasp);
+    *reinterpret_cast<uint4*>(&b[4]) = *reinterpret_cast<const uint4*>(biasp + 8);
+  }
+  if (EV == EV_GATE_RES) {
+    *reinterpret_cast<uint4*>(&g[0]) = *reinterpret_cast<const uint4*>(gatep);
+    *reinterpret_cast<uint4*>(&g[4]) = *reinterpret_cast<const uint4*>(gatep + 8);
+  }
+  if (EV == EV_GATE_RES || EV == EV_RES) {
+    *reinterpret_cast<uint4*>(&r[0]) = *reinterpret_cast<const uint4*>(resp);
+    *reinterpret_cast<uint4*>(&r[4]) = *reinterpret_cast<const uint4*>(resp + 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float a0 = __uint_as_float(acc[2 * i]), a1 = __uint_as_float(acc[2 * i + 1]);
+    bf162 v;
+    if (BIAS == BIAS_FUSED) {  // bias enters the fp32 accumulator (cuBLASLt C operand, beta = 1): one rounding
+      v = __floats2bfloat162_rn(a0 + bf_lo(b[i]), a1 + bf_hi(b[i]));
+    } else {
+      v = __floats2bfloat162_rn(a0, a1);
+      if (BIAS == BIAS_AFTER_ROUND) v = __hadd2(v, as_bf162(b[i]));  // separate bf16 broadcast_add
+    }
+    if (EV == EV_ALPHA) v = __hmul2(v, alpha2);
+    if (EV == EV_GELU) v = gelu_bf16x2(v);
+    if (EV == EV_GATE_RES) v = __hmul2(as_bf162(g[i]), v);
+    if (EV == EV_GATE_RES || EV == EV_RES) v = __hadd2(as_bf162(r[i]), v);
+    o[i] = as_u32(v);
+  }
+  *reinterpret_cast<uint4*>(outp) = *reinterpret_cast<uint4*>(&o[0]);
+  *reinterpret_cast<uint4*>(outp + 8) = *reinterpret_cast<uint4*>(&o[4]);
+}
+
+// generic per-element fallback for ragged N (final proj N=64 tail-free, conv_out N=3, ...): runtime flags
+__device__ __noinline__ void epi_slow(const uint32_t* acc, int ncols, bf16* outp, const bf16* biasp, int bias_mode,
+                                      int ev, const bf16* gatep, const bf16* resp, float alpha) {
+  for (int e = 0; e < ncols; ++e) {
+    float v = __uint_as_float(acc[e]);
+    const float bv = biasp ? __bfloat162float(biasp[e]) : 0.f;
+    if (bias_mode == BIAS_FUSED) {
+      v = rbf(v + bv);
+    } else {
+      v = rbf(v);
+      if (bias_mode == BIAS_AFTER_ROUND) v = rbf(v + bv);
+    }
+    if (ev == EV_ALPHA) v = rbf(v * alpha);
+    if (ev == EV_GELU) v = gelu_bf16_steps(v);
+    if (ev == EV_GATE_RES) v = rbf(__bfloat162float(gatep[e]) * v);
+    if (ev == EV_GATE_RES || ev == EV_RES) v = rbf(__bfloat162float(resp[e]) + v);
+    outp[e] = __float2bfloat16_rn(v);
+  }
 }
 
 struct TileCoord {
@@ -118,7 +205,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 4);  // one arrival per epilogue warp
+      mbar_init(&tmem_empty[s], EPI_WARPS);  // one arrival per epilogue warp
     }
     fence_barrier_init();
   }
@@ -206,8 +293,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       }
     }
   } else {
-    // ================= epilogue warps =================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ================= epilogue warps (2..9) =================
+    const int q = warp & 3;              // TMEM lane quarter this warp may access (hardware: warp_id % 4)
+    const int chalf = (warp - 2) >> 2;   // which 128-column half of the tile this warp drains
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
@@ -230,14 +318,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       }
       const long long gate_off =
           (p.gate != nullptr) ? (p.rows_per_batch > 0 ? grow / p.rows_per_batch : 0) * p.gate_bstride : 0;
+      const bf162 alpha2 = __float2bfloat162_rn(p.alpha);
+      const int bias_mode = p.bias_mode;
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
+      const uint32_t t_row = tmem_base + acc * BLOCK_N + chalf * 128 + (static_cast<uint32_t>(q * 32) << 16);
 
 #pragma unroll 1
-      for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
-        const int n0 = tc.n_t * BLOCK_N + chunk * 32;
+      for (int chunk = 0; chunk < 4; ++chunk) {
+        const int n0 = tc.n_t * BLOCK_N + chalf * 128 + chunk * 32;
         if (n0 >= p.N) break;  // warp-uniform
         uint32_t acc_r[32];
         tmem_ld32(t_row + chunk * 32, acc_r);
@@ -245,69 +335,31 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
         if (!valid) continue;
         const bool seg1 = (p.n_split > 0) && (n0 >= p.n_split);
         bf16* outp = seg1 ? p.out1 + grow * p.ld1 + (n0 - p.n_split + p.col_off1) : p.out0 + grow * p.ld0 + n0;
-        const int act = seg1 ? p.act1 : p.act0;
-        const bf16* resp = (p.res != nullptr && !seg1) ? p.res + grow * p.ld0 + n0 : nullptr;
-        const bf16* gatep = (p.gate != nullptr && !seg1) ? p.gate + gate_off + n0 : nullptr;
-        const bf16* biasp = (p.bias_mode != BIAS_NONE) ? p.bias + n0 : nullptr;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int nj = n0 + j * 8;
-          if (nj >= p.N) break;
-          const bool full8 = (nj + 8 <= p.N);
-          float bv[8], gv[8], rv[8];
-          if (full8) {
-            if (biasp) {
-              uint4 u = *reinterpret_cast<const uint4*>(biasp + j * 8);
-              bv[0] = bf_lo(u.x), bv[1] = bf_hi(u.x), bv[2] = bf_lo(u.y), bv[3] = bf_hi(u.y);
-              bv[4] = bf_lo(u.z), bv[5] = bf_hi(u.z), bv[6] = bf_lo(u.w), bv[7] = bf_hi(u.w);
-            }
-            if (gatep) {
-              uint4 u = *reinterpret_cast<const uint4*>(gatep + j * 8);
-              gv[0] = bf_lo(u.x), gv[1] = bf_hi(u.x), gv[2] = bf_lo(u.y), gv[3] = bf_hi(u.y);
-              gv[4] = bf_lo(u.z), gv[5] = bf_hi(u.z), gv[6] = bf_lo(u.w), gv[7] = bf_hi(u.w);
-            }
-            if (resp) {
-              uint4 u = *reinterpret_cast<const uint4*>(resp + j * 8);
-              rv[0] = bf_lo(u.x), rv[1] = bf_hi(u.x), rv[2] = bf_lo(u.y), rv[3] = bf_hi(u.y);
-              rv[4] = bf_lo(u.z), rv[5] = bf_hi(u.z), rv[6] = bf_lo(u.w), rv[7] = bf_hi(u.w);
-            }
-          } else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const bool in = nj + e < p.N;
-              bv[e] = (biasp && in) ? __bfloat162float(biasp[j * 8 + e]) : 0.f;
-              gv[e] = (gatep && in) ? __bfloat162float(gatep[j * 8 + e]) : 0.f;
-              rv[e] = (resp && in) ? __bfloat162float(resp[j * 8 + e]) : 0.f;
-            }
+        const int ev = seg1 ? p.ev1 : p.ev0;
+        const bf16* resp = (ev == EV_RES || ev == EV_GATE_RES) ? p.res + grow * p.ld0 + n0 : nullptr;
+        const bf16* gatep = (ev == EV_GATE_RES) ? p.gate + gate_off + n0 : nullptr;
+        const bf16* biasp = (bias_mode != BIAS_NONE) ? p.bias + n0 : nullptr;
+        if (n0 + 32 <= p.N) {
+          // warp-uniform dispatch to a fully specialised 2 x 16-column body
+#define FB_EPI_CASE(B, E)                                                                  \
+  case (B) * EV_KINDS + (E):                                                               \
+    epi16<B, E>(acc_r, outp, biasp, gatep, resp, alpha2);                                  \
+    epi16<B, E>(acc_r + 16, outp + 16, biasp ? biasp + 16 : nullptr, gatep ? gatep + 16 : nullptr, \
+                resp ? resp + 16 : nullptr, alpha2);                                       \
+    break;
+#define FB_EPI_BIAS(B) \
+  FB_EPI_CASE(B, EV_PLAIN) FB_EPI_CASE(B, EV_GELU) FB_EPI_CASE(B, EV_RES) FB_EPI_CASE(B, EV_GATE_RES) FB_EPI_CASE(B, EV_ALPHA)
+          switch (bias_mode * EV_KINDS + ev) {
+            FB_EPI_BIAS(BIAS_NONE)
+            FB_EPI_BIAS(BIAS_FUSED)
+            FB_EPI_BIAS(BIAS_AFTER_ROUND)
+            default:
+              break;
           }
-          float o[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            float v = __uint_as_float(acc_r[j * 8 + e]);
-            if (p.bias_mode == BIAS_FUSED) {
-              v = rbf(v + bv[e]);  // bias enters the fp32 accumulator (cuBLASLt C operand, beta = 1)
-            } else {
-              v = rbf(v);
-              if (p.bias_mode == BIAS_AFTER_ROUND) v = rbf(v + bv[e]);  // separate bf16 broadcast_add
-            }
-            if (p.has_alpha) v = rbf(v * p.alpha);
-            if (act == ACT_GELU) v = gelu_bf16_steps(v);
-            if (gatep) v = rbf(gv[e] * v);
-            if (resp) v = rbf(rv[e] + v);
-            o[e] = v;
-          }
-          if (full8) {
-            uint4 u;
-            u.x = pack_bf16(o[0], o[1]);
-            u.y = pack_bf16(o[2], o[3]);
-            u.z = pack_bf16(o[4], o[5]);
-            u.w = pack_bf16(o[6], o[7]);
-            *reinterpret_cast<uint4*>(outp + j * 8) = u;
-          } else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e)
-              if (nj + e < p.N) outp[j * 8 + e] = __float2bfloat16_rn(o[e]);
-          }
+#undef FB_EPI_BIAS
+#undef FB_EPI_CASE
+        } else {
+          epi_slow(acc_r, p.N - n0, outp, biasp, bias_mode, ev, gatep, resp, p.alpha);
         }
       }
       // release the accumulator back to the MMA warp
@@ -390,10 +442,26 @@ int launch_gemm(const GemmDesc* descs, int count, cudaStream_t stream) {
     tile += p.tiles_m * p.tiles_n;
     p.tile_end = tile;
     p.out0 = d.out0, p.ld0 = d.ld0, p.out1 = d.out1, p.ld1 = d.ld1;
-    p.n_split = d.n_split, p.col_off1 = d.col_off1, p.act0 = d.act0, p.act1 = d.act1;
+    p.n_split = d.n_split, p.col_off1 = d.col_off1;
+    {
+      const bool has_alpha = d.alpha != 1.0f;
+      FB_REQUIRE(!(d.gate && !d.res), "launch_gemm: gate without residual is not supported");
+      FB_REQUIRE(!(d.act0 == ACT_GELU && (d.res || has_alpha)), "launch_gemm: GELU cannot be combined with residual/alpha");
+      FB_REQUIRE(!(has_alpha && d.res), "launch_gemm: alpha cannot be combined with a residual");
+      p.ev0 = d.act0 == ACT_GELU ? EV_GELU : (d.gate ? EV_GATE_RES : (d.res ? EV_RES : (has_alpha ? EV_ALPHA : EV_PLAIN)));
+      p.ev1 = d.act1 == ACT_GELU ? EV_GELU : EV_PLAIN;
+      if (p.ev0 == EV_GATE_RES || p.ev0 == EV_RES) {
+        FB_REQUIRE((reinterpret_cast<uintptr_t>(d.res) & 15) == 0 && d.ld0 % 8 == 0, "launch_gemm: residual alignment");
+        if (d.gate)
+          FB_REQUIRE((reinterpret_cast<uintptr_t>(d.gate) & 15) == 0 && d.gate_bstride % 8 == 0, "launch_gemm: gate alignment");
+      }
+      if (d.bias_mode != BIAS_NONE)
+        FB_REQUIRE((reinterpret_cast<uintptr_t>(d.bias) & 15) == 0, "launch_gemm: bias must be 16-byte aligned");
+    }
     p.bias = d.bias, p.bias_mode = d.bias_mode;
     p.gate = d.gate, p.gate_bstride = d.gate_bstride, p.rows_per_batch = d.rows_per_batch, p.res = d.res;
     p.alpha = d.alpha, p.has_alpha = (d.alpha != 1.0f);
+    if (d.N % 8 == 0) FB_REQUIRE(d.ld0 % 8 == 0, "launch_gemm: ldo must be a multiple of 8");
   }
   P.total_tiles = tile;
   double flops = 0, bytes = 0;

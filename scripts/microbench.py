@@ -19,6 +19,7 @@ def timeit(fn, iters=10, warm=3):
     ts = []
     for _ in range(iters):
         flush.zero_()
+        torch.cuda._sleep(2_000_000)  # ~1 ms spin kernel: the launches below queue behind it, so a->b has no host gaps
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         fn()
