@@ -29,7 +29,7 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 // (models/flux/model.rs:217-221). One warp per row, the row stays in registers between the two passes.
 // ------------------------------------------------------------------------------------------------
 template <int D>
-__global__ void __launch_bounds__(128) ln_modulate_kernel(const bf16* __restrict__ x, long long in_bstride_rows,
+__global__ void __launch_bounds__(128, 4) ln_modulate_kernel(const bf16* __restrict__ x, long long in_bstride_rows,
                                                           int in_row_off, int rows_per_batch, int total_rows,
                                                           const bf16* __restrict__ shift,
                                                           const bf16* __restrict__ scale, long long mod_bstride,
@@ -41,16 +41,18 @@ __global__ void __launch_bounds__(128) ln_modulate_kernel(const bf16* __restrict
   const int b = row / rows_per_batch;
   const int i = row - b * rows_per_batch;
   const bf16* xr = x + (static_cast<long long>(b) * in_bstride_rows + in_row_off + i) * D;
-  float v[VEC][8];
+  uint4 u[VEC];  // the row stays packed in registers (48 regs) so that >= 5 blocks fit on an SM
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) u[k] = *reinterpret_cast<const uint4*>(xr + (k * 32 + lane) * 8);
   float s = 0.f, s2 = 0.f;
 #pragma unroll
   for (int k = 0; k < VEC; ++k) {
-    uint4 u = *reinterpret_cast<const uint4*>(xr + (k * 32 + lane) * 8);
-    unpack8(u, v[k]);
+    float v[8];
+    unpack8(u[k], v);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      s += v[k][e];
-      s2 += v[k][e] * v[k][e];
+      s += v[e];
+      s2 += v[e] * v[e];
     }
   }
   s = warp_sum(s);
@@ -64,12 +66,13 @@ __global__ void __launch_bounds__(128) ln_modulate_kernel(const bf16* __restrict
 #pragma unroll
   for (int k = 0; k < VEC; ++k) {
     const int c = (k * 32 + lane) * 8;
-    float fs[8], fc[8], o[8];
+    float v[8], fs[8], fc[8], o[8];
+    unpack8(u[k], v);
     unpack8(*reinterpret_cast<const uint4*>(sh + c), fs);
     unpack8(*reinterpret_cast<const uint4*>(sc + c), fc);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      float n = rbf((v[k][e] - mean) * inv_std);
+      float n = rbf((v[e] - mean) * inv_std);
       float m = rbf(n * rbf(fc[e] + 1.0f));
       o[e] = rbf(m + fs[e]);
     }
@@ -96,56 +99,57 @@ int launch_ln_modulate(const bf16* x, long long in_bstride_rows, int in_row_off,
 //   out: Q, K, V [B, H, L, 128]; the stream's tokens land at sequence offset l_off (txt first, then img)
 // reference: SelfAttention::qkv (model.rs:399-427), RmsNorm slow path (nn/layer_norm.rs:136-153),
 //            apply_rope (model.rs:86-95): out0 = cos*x0 + (-sin)*x1, out1 = sin*x0 + cos*x1, every op rounded to bf16.
-// One warp per (token, head, q|k|v): 128 contiguous bf16 = 8 B per lane.
+// One block per token; 16 lanes per head (8 elements = 16 B each); every thread owns the same 8 columns of q, k and v
+// of its head, so the three 16-byte loads are in flight together and the RoPE factors are loaded once.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) qknorm_rope_kernel(const bf16* __restrict__ qkv, long long ld,
+__global__ void __launch_bounds__(512) qknorm_rope_kernel(const bf16* __restrict__ qkv, long long ld,
                                                           int rows_per_batch, int H, int L, int l_off,
                                                           const bf16* __restrict__ wq, const bf16* __restrict__ wk,
                                                           const bf16* __restrict__ pe_cos,
                                                           const bf16* __restrict__ pe_sin, long long pe_bstride,
                                                           bf16* __restrict__ Q,
                                                           bf16* __restrict__ K, bf16* __restrict__ V, float eps) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x;
+  const int h = threadIdx.x >> 4;   // head
+  const int sub = threadIdx.x & 15; // 8-column group inside the head
+  if (h >= H) return;
   const int b = row / rows_per_batch;
   const int l = l_off + (row - b * rows_per_batch);
   const int D = H * 128;
-  const bf16* base = qkv + static_cast<long long>(row) * ld;
-  for (int item = warp; item < 3 * H; item += 8) {
-    const int which = item / H;  // 0 q, 1 k, 2 v
-    const int h = item - which * H;
-    const uint2 u = *reinterpret_cast<const uint2*>(base + which * D + h * 128 + lane * 4);
-    bf16* dst = (which == 0 ? Q : (which == 1 ? K : V)) + ((static_cast<long long>(b) * H + h) * L + l) * 128 + lane * 4;
-    if (which == 2) {
-      *reinterpret_cast<uint2*>(dst) = u;
-      continue;
-    }
-    float x[4] = {bf_lo(u.x), bf_hi(u.x), bf_lo(u.y), bf_hi(u.y)};
-    float ss = x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3];
-    ss = warp_sum(ss);
+  const bf16* base = qkv + static_cast<long long>(row) * ld + h * 128 + sub * 8;
+  const uint4 uq = *reinterpret_cast<const uint4*>(base);
+  const uint4 uk = *reinterpret_cast<const uint4*>(base + D);
+  const uint4 uv = *reinterpret_cast<const uint4*>(base + 2 * D);
+  const long long pe_off = b * pe_bstride + static_cast<long long>(l) * 64 + sub * 4;
+  const uint2 cu = *reinterpret_cast<const uint2*>(pe_cos + pe_off);
+  const uint2 su = *reinterpret_cast<const uint2*>(pe_sin + pe_off);
+  const uint4 wqu = *reinterpret_cast<const uint4*>(wq + sub * 8);
+  const uint4 wku = *reinterpret_cast<const uint4*>(wk + sub * 8);
+  const long long dst_off = ((static_cast<long long>(b) * H + h) * L + l) * 128 + sub * 8;
+  *reinterpret_cast<uint4*>(V + dst_off) = uv;
+  const float c[4] = {bf_lo(cu.x), bf_hi(cu.x), bf_lo(cu.y), bf_hi(cu.y)};
+  const float sn[4] = {bf_lo(su.x), bf_hi(su.x), bf_lo(su.y), bf_hi(su.y)};
+#pragma unroll
+  for (int which = 0; which < 2; ++which) {
+    float x[8], wf[8], o[8];
+    unpack8(which == 0 ? uq : uk, x);
+    unpack8(which == 0 ? wqu : wku, wf);
+    float ss = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) ss += x[e] * x[e];
+#pragma unroll
+    for (int m = 8; m > 0; m >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, m);  // 16-lane groups
     const float denom = sqrtf(ss / 128.0f + eps);
-    const bf16* w = (which == 0 ? wq : wk) + lane * 4;
-    const uint2 wu = *reinterpret_cast<const uint2*>(w);
-    const float wf[4] = {bf_lo(wu.x), bf_hi(wu.x), bf_lo(wu.y), bf_hi(wu.y)};
-    float y[4];
+    float y[8];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) y[e] = rbf(rbf(x[e] / denom) * wf[e]);
-    // rope: pairs (2i, 2i+1), i = lane*2 + {0,1}
-    const uint32_t cu = *reinterpret_cast<const uint32_t*>(pe_cos + b * pe_bstride + static_cast<long long>(l) * 64 + lane * 2);
-    const uint32_t su = *reinterpret_cast<const uint32_t*>(pe_sin + b * pe_bstride + static_cast<long long>(l) * 64 + lane * 2);
-    const float c[2] = {bf_lo(cu), bf_hi(cu)};
-    const float s[2] = {bf_lo(su), bf_hi(su)};
-    float o[4];
+    for (int e = 0; e < 8; ++e) y[e] = rbf(rbf(x[e] / denom) * wf[e]);
 #pragma unroll
-    for (int p = 0; p < 2; ++p) {
+    for (int p = 0; p < 4; ++p) {  // pairs (2i, 2i+1), i = sub*4 + p
       const float x0 = y[2 * p], x1 = y[2 * p + 1];
-      o[2 * p] = rbf(rbf(c[p] * x0) + rbf(-s[p] * x1));
-      o[2 * p + 1] = rbf(rbf(s[p] * x0) + rbf(c[p] * x1));
+      o[2 * p] = rbf(rbf(c[p] * x0) + rbf(-sn[p] * x1));
+      o[2 * p + 1] = rbf(rbf(sn[p] * x0) + rbf(c[p] * x1));
     }
-    uint2 ou;
-    ou.x = pack_bf16(o[0], o[1]);
-    ou.y = pack_bf16(o[2], o[3]);
-    *reinterpret_cast<uint2*>(dst) = ou;
+    *reinterpret_cast<uint4*>((which == 0 ? Q : K) + dst_off) = pack8(o);
   }
 }
 
@@ -155,7 +159,8 @@ int launch_qknorm_rope(const bf16* qkv, long long ld, int rows_per_batch, int ba
   const int rows = rows_per_batch * batch;
   ProfScope _ps(KK_QKNORM_ROPE, 0, 12.0 * rows * H * 128, stream);
   count_launch(KK_QKNORM_ROPE, 1);
-  qknorm_rope_kernel<<<rows, 256, 0, stream>>>(qkv, ld, rows_per_batch, H, L, l_off, wq, wk, pe_cos, pe_sin,
+  FB_REQUIRE(H >= 1 && H <= 32, "qknorm_rope: 1..32 heads");
+  qknorm_rope_kernel<<<rows, H * 16, 0, stream>>>(qkv, ld, rows_per_batch, H, L, l_off, wq, wk, pe_cos, pe_sin,
                                                pe_bstride, Q, K, V, eps);
   FB_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -24,22 +24,29 @@ namespace fb {
 static constexpr int BLOCK_M = 128;
 static constexpr int BLOCK_N = 256;
 static constexpr int BLOCK_K = 64;
-static constexpr int STAGES = 4;
 static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
-static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;  // 32 KB
-static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+// CTA2 = a CTA pair (cta_group::2) computes one 256x256 tile: each CTA stages its own 128 rows of A and HALF of the
+// 256 W rows, the MMA (M=256, issued by the leader) reads both halves -> 1.5x less L2->SM traffic per FLOP.
+template <bool CTA2>
+struct GemmCfg {
+  static constexpr int B_ROWS = CTA2 ? BLOCK_N / 2 : BLOCK_N;
+  static constexpr int B_BYTES = B_ROWS * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;  // 32 KB (pair) / 48 KB (single)
+  static constexpr int STAGES = CTA2 ? 6 : 4;
+  static constexpr size_t SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
 static constexpr int GEMM_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 static constexpr int EPI_WARPS = 8;
 static constexpr int MAX_PROBLEMS = 4;
 static constexpr int GROUP_M = 8;
 static constexpr int CONV_TH = 8, CONV_TW = 16;  // 8x16 output pixels = one 128-row M tile
-static constexpr size_t GEMM_SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 
 struct alignas(64) GemmProblemDev {
   CUtensorMap tmap_a;
   CUtensorMap tmap_b;
   int M, N, K, num_kb;
   int tiles_m, tiles_n, tile_begin, tile_end;
+  int sched_m;  // scheduling units along M: tiles_m (single CTA) or ceil(tiles_m / 2) (CTA pair)
   int conv, cH, cW, cC, c_chunks, ksize, tiles_h, tiles_w;
   bf16* out0;
   bf16* out1;
@@ -172,7 +179,7 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& P, int t) {
   int group_size = GROUP_M * p.tiles_n;
   int g = lt / group_size;
   int first_m = g * GROUP_M;
-  int gm = min(p.tiles_m - first_m, GROUP_M);
+  int gm = min(p.sched_m - first_m, GROUP_M);
   int in_g = lt - g * group_size;
   TileCoord c;
   c.prob = pi;
@@ -181,7 +188,14 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& P, int t) {
   return c;
 }
 
+template <bool CTA2>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams P) {
+  using Cfg = GemmCfg<CTA2>;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int STAGE_BYTES = Cfg::STAGE_BYTES;
+  const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0;       // rank inside the CTA pair
+  const int unit_id = CTA2 ? (blockIdx.x >> 1) : blockIdx.x;    // tile-scheduling unit (CTA or CTA pair)
+  const int num_units = CTA2 ? (gridDim.x >> 1) : gridDim.x;
   extern __shared__ uint8_t smem_raw[];
   // 128B swizzle needs 1024-byte aligned tiles
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -205,13 +219,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], EPI_WARPS);  // one arrival per epilogue warp
+      mbar_init(&tmem_empty[s], CTA2 ? 2 * EPI_WARPS : EPI_WARPS);  // one arrival per epilogue warp (of both CTAs)
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_base_slot, 512);
+  if (warp == 1) {
+    if (CTA2) tmem_alloc_2sm(tmem_base_slot, 512); else tmem_alloc(tmem_base_slot, 512);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (CTA2) cluster_sync_all(); else __syncthreads();  // peer barriers must be initialised before remote arrivals
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
 
@@ -220,14 +236,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
+      for (int t = unit_id; t < P.total_tiles; t += num_units) {
         TileCoord tc = decode_tile(P, t);
         const GemmProblemDev& p = P.p[tc.prob];
+        const int m_t = CTA2 ? 2 * tc.m_t + static_cast<int>(cta_rank) : tc.m_t;
+        const int b_row0 = tc.n_t * BLOCK_N + (CTA2 ? static_cast<int>(cta_rank) * Cfg::B_ROWS : 0);
         int cn = 0, ch0 = 0, cw0 = 0;
         if (p.conv) {
           int per_img = p.tiles_h * p.tiles_w;
-          cn = tc.m_t / per_img;
-          int rem = tc.m_t - cn * per_img;
+          cn = m_t / per_img;
+          int rem = m_t - cn * per_img;
           ch0 = (rem / p.tiles_w) * CONV_TH;
           cw0 = (rem % p.tiles_w) * CONV_TW;
         }
@@ -235,17 +253,30 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+          int a_c0, b_c0;
+          int tap = 0, kh = 0, kw = 0, pad = 0;
           if (p.conv) {
-            int tap = kb / p.c_chunks;
-            int cc = kb - tap * p.c_chunks;
-            int kh = tap / p.ksize, kw = tap - kh * p.ksize;
-            int pad = p.ksize >> 1;
-            tma_load_4d(sa, &p.tmap_a, &full_bar[stage], cc * BLOCK_K, cw0 + kw - pad, ch0 + kh - pad, cn);
-            tma_load_2d(sb, &p.tmap_b, &full_bar[stage], tap * p.cC + cc * BLOCK_K, tc.n_t * BLOCK_N);
+            tap = kb / p.c_chunks;
+            const int cc = kb - tap * p.c_chunks;
+            kh = tap / p.ksize, kw = tap - kh * p.ksize;
+            pad = p.ksize >> 1;
+            a_c0 = cc * BLOCK_K;
+            b_c0 = tap * p.cC + cc * BLOCK_K;
           } else {
-            tma_load_2d(sa, &p.tmap_a, &full_bar[stage], kb * BLOCK_K, tc.m_t * BLOCK_M);
-            tma_load_2d(sb, &p.tmap_b, &full_bar[stage], kb * BLOCK_K, tc.n_t * BLOCK_N);
+            a_c0 = b_c0 = kb * BLOCK_K;
+          }
+          if (CTA2) {
+            // both CTAs' bytes are credited to the leader's barrier; only the leader arms it
+            const uint32_t bar = mapa_u32(smem_u32(&full_bar[stage]), 0);
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+            if (p.conv) tma_load_4d_2sm(sa, &p.tmap_a, bar, a_c0, cw0 + kw - pad, ch0 + kh - pad, cn);
+            else        tma_load_2d_2sm(sa, &p.tmap_a, bar, a_c0, m_t * BLOCK_M);
+            tma_load_2d_2sm(sb, &p.tmap_b, bar, b_c0, b_row0);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+            if (p.conv) tma_load_4d(sa, &p.tmap_a, &full_bar[stage], a_c0, cw0 + kw - pad, ch0 + kh - pad, cn);
+            else        tma_load_2d(sa, &p.tmap_a, &full_bar[stage], a_c0, m_t * BLOCK_M);
+            tma_load_2d(sb, &p.tmap_b, &full_bar[stage], b_c0, b_row0);
           }
           if (++stage == STAGES) {
             stage = 0;
@@ -255,14 +286,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer (single thread) =================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N);
+    // ================= MMA issuer (single thread; in pair mode only the leader CTA issues) =================
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(CTA2 ? 2 * BLOCK_M : BLOCK_M, BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
+      for (int t = unit_id; t < P.total_tiles; t += num_units) {
         TileCoord tc = decode_tile(P, t);
         const GemmProblemDev& p = P.p[tc.prob];
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -277,15 +308,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
 #pragma unroll
           for (int k = 0; k < BLOCK_K / 16; ++k) {
             // advance 16 bf16 = 32 B along K inside the 128B swizzle atom: +2 in the (addr >> 4) field
-            umma_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            if (CTA2) umma_ss_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            else      umma_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
           }
-          tc_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          // frees the smem slot (in both CTAs) once these MMAs have read it
+          if (CTA2) tc_commit_2sm(&empty_bar[stage], 3); else tc_commit(&empty_bar[stage]);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        tc_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue warps (of both CTAs)
+        if (CTA2) tc_commit_2sm(&tmem_full[acc], 3); else tc_commit(&tmem_full[acc]);
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -298,22 +332,23 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     const int chalf = (warp - 2) >> 2;   // which 128-column half of the tile this warp drains
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
+    for (int t = unit_id; t < P.total_tiles; t += num_units) {
       TileCoord tc = decode_tile(P, t);
       const GemmProblemDev& p = P.p[tc.prob];
+      const int m_t = CTA2 ? 2 * tc.m_t + static_cast<int>(cta_rank) : tc.m_t;
       const int r = q * 32 + lane;  // row inside the tile == TMEM lane
       long long grow;
       bool valid;
       if (p.conv) {
         int per_img = p.tiles_h * p.tiles_w;
-        int cn = tc.m_t / per_img;
-        int rem = tc.m_t - cn * per_img;
+        int cn = m_t / per_img;
+        int rem = m_t - cn * per_img;
         int h = (rem / p.tiles_w) * CONV_TH + r / CONV_TW;
         int w = (rem % p.tiles_w) * CONV_TW + r % CONV_TW;
-        valid = (h < p.cH) && (w < p.cW);
+        valid = (m_t < p.tiles_m) && (h < p.cH) && (w < p.cW);
         grow = (static_cast<long long>(cn) * p.cH + h) * p.cW + w;
       } else {
-        grow = static_cast<long long>(tc.m_t) * BLOCK_M + r;
+        grow = static_cast<long long>(m_t) * BLOCK_M + r;
         valid = grow < p.M;
       }
       const long long gate_off =
@@ -365,7 +400,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       // release the accumulator back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) {
+        if (CTA2) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));  // the leader's MMA thread waits on it
+        else      mbar_arrive(&tmem_empty[acc]);
+      }
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
@@ -374,10 +412,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CTA2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (CTA2) tmem_dealloc_2sm(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -387,11 +425,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
 int launch_gemm(const GemmDesc* descs, int count, cudaStream_t stream) {
   FB_REQUIRE(count >= 1 && count <= MAX_PROBLEMS, "launch_gemm: 1..4 problems per launch");
   static bool attr_set = false;
+  static bool use_pair = true;
   if (!attr_set) {
-    FB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(GEMM_SMEM)));
+    FB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(GemmCfg<false>::SMEM)));
+    FB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(GemmCfg<true>::SMEM)));
+    const char* e = getenv("FLUXB200_GEMM_SINGLE_CTA");  // A/B switch: 1 -> cta_group::1 kernel
+    use_pair = !(e && e[0] == '1');
     attr_set = true;
   }
+  const int b_box_rows = use_pair ? GemmCfg<true>::B_ROWS : GemmCfg<false>::B_ROWS;
   GemmParams P;
   memset(&P, 0, sizeof(P));
   P.count = count;
@@ -434,12 +478,13 @@ int launch_gemm(const GemmDesc* descs, int count, cudaStream_t stream) {
     }
     FB_REQUIRE(d.ldb % 8 == 0, "launch_gemm: ldb must be a multiple of 8");
     {
-      int rc = encode_tmap_2d(&p.tmap_b, d.w, d.K, d.N, static_cast<uint64_t>(d.ldb) * 2, BLOCK_K, BLOCK_N);
+      int rc = encode_tmap_2d(&p.tmap_b, d.w, d.K, d.N, static_cast<uint64_t>(d.ldb) * 2, BLOCK_K, b_box_rows);
       if (rc) return rc;
     }
     p.tiles_n = (d.N + BLOCK_N - 1) / BLOCK_N;
+    p.sched_m = use_pair ? (p.tiles_m + 1) / 2 : p.tiles_m;
     p.tile_begin = tile;
-    tile += p.tiles_m * p.tiles_n;
+    tile += p.sched_m * p.tiles_n;
     p.tile_end = tile;
     p.out0 = d.out0, p.ld0 = d.ld0, p.out1 = d.out1, p.ld1 = d.ld1;
     p.n_split = d.n_split, p.col_off1 = d.col_off1;
@@ -472,8 +517,21 @@ int launch_gemm(const GemmDesc* descs, int count, cudaStream_t stream) {
   }
   ProfScope _ps(KK_GEMM, flops, bytes, stream);
   count_launch(KK_GEMM);
-  int grid = std::min(tile, num_sms());
-  gemm_tcgen05_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(P);
+  if (use_pair) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * std::min(tile, num_sms() / 2));
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = GemmCfg<true>::SMEM;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    FB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<true>, P));
+  } else {
+    const int grid = std::min(tile, num_sms());
+    gemm_tcgen05_kernel<false><<<grid, GEMM_THREADS, GemmCfg<false>::SMEM, stream>>>(P);
+  }
   FB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
