@@ -6,7 +6,8 @@
 // One CTA = one (batch, head) x 256 query rows (two 128-row tiles that ping-pong on the tensor core):
 //   warp 0       TMA producer: Q0,Q1 once; K_j, V_j through 2-stage rings (128B swizzle)
 //   warp 1       MMA issuer  : S_g = Q_g.K_j^T (SS) and O_g += P_g.V_j (A = P from TMEM, B = V MN-major from smem)
-//   warps 2..5   softmax for tile 0, warps 6..9 softmax for tile 1: one thread per query row, online softmax in
+//   warps 2..5   softmax for tile 0, warps 6..9 softmax for tile 1 (ping-pong on the MUFU unit through a pair of
+//                named barriers): one thread per query row, online softmax in
 //                fp32 with lazy rescaling of the TMEM-resident O accumulator; P is written back to TMEM as bf16
 //                over the S columns it came from.
 // TMEM: S0 [0,128) S1 [128,256) O0 [256,384) O1 [384,512) fp32 columns.
@@ -21,6 +22,7 @@ static constexpr int TKV = 128;           // kv rows per block
 static constexpr int TILE_BYTES = TQ * HD * 2;   // 32 KB (two 16 KB swizzle-atom columns)
 static constexpr int HALF_BYTES = TILE_BYTES / 2;
 static constexpr int ATT_THREADS = 320;
+static constexpr bool PINGPONG = true;
 static constexpr size_t ATT_SMEM = 6 * TILE_BYTES + 1024 + 256;
 
 struct AttnParams {
@@ -105,25 +107,35 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tcgen05_kernel(const
       // ---------------- MMA issuer ----------------
       constexpr uint32_t idesc_s = umma_idesc_bf16(TQ, TKV, 0, 0);  // Q (K-major) x K (K-major)
       constexpr uint32_t idesc_o = umma_idesc_bf16(TQ, HD, 0, 1);   // P (TMEM)    x V (MN-major)
-      const uint32_t q_addr = smem_u32(sQ);
+      // The issuing thread is a single lane: keep its instruction stream short.  All shared-memory descriptors are
+      // built once; inside the loops a descriptor is `base + compile-time constant` (the address field is the low
+      // 14 bits in 16-byte units and smem < 256 KB, so the add never carries into the next field).
+      const uint64_t qd0 = umma_smem_desc_sw128(smem_u32(sQ), 16, 1024);
+      const uint64_t qd1 = umma_smem_desc_sw128(smem_u32(sQ) + TILE_BYTES, 16, 1024);
+      const uint64_t kd0 = umma_smem_desc_sw128(smem_u32(sK), 16, 1024);
+      const uint64_t kd1 = umma_smem_desc_sw128(smem_u32(sK) + TILE_BYTES, 16, 1024);
+      const uint64_t vd0 = umma_smem_desc_sw128(smem_u32(sV), HALF_BYTES, 1024);
+      const uint64_t vd1 = umma_smem_desc_sw128(smem_u32(sV) + TILE_BYTES, HALF_BYTES, 1024);
       auto issue_s = [&](int g, int st) {
-        const uint32_t qa = q_addr + g * TILE_BYTES;
-        const uint32_t ka = smem_u32(sK) + st * TILE_BYTES;
+        const uint64_t qd = g ? qd1 : qd0;
+        const uint64_t kd = st ? kd1 : kd0;
+        const uint32_t ts = tmem_base + g * 128;
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k) {
-          const uint32_t off = (k >> 2) * HALF_BYTES + (k & 3) * 32;
-          umma_ss(tmem_base + g * 128, umma_smem_desc_sw128(qa + off, 16, 1024),
-                  umma_smem_desc_sw128(ka + off, 16, 1024), idesc_s, k != 0);
+          // d 0..63 sit in the first swizzle-atom column, 64..127 in the second; 32 B per k-step inside an atom
+          const uint64_t off = static_cast<uint64_t>(((k >> 2) * HALF_BYTES + (k & 3) * 32) >> 4);
+          umma_ss(ts, qd + off, kd + off, idesc_s, k != 0);
         }
       };
       auto issue_pv = [&](int g, int st, bool accumulate) {
-        const uint32_t va = smem_u32(sV) + st * TILE_BYTES;
+        const uint64_t vd = st ? vd1 : vd0;
+        const uint32_t to = tmem_base + 256 + g * 128;
+        const uint32_t tp = tmem_base + g * 128;
 #pragma unroll
         for (int k = 0; k < TKV / 16; ++k) {
           // A: 16 bf16 of P per row = 8 TMEM columns per k-step. B: 16 kv rows = 2048 B per k-step;
           // the two 64-wide d chunks are HALF_BYTES apart (LBO), 8-row groups 1024 B apart (SBO).
-          umma_ts(tmem_base + 256 + g * 128, tmem_base + g * 128 + k * 8,
-                  umma_smem_desc_sw128(va + k * 2048, HALF_BYTES, 1024), idesc_o, accumulate || (k != 0));
+          umma_ts(to, tp + k * 8, vd + static_cast<uint64_t>((k * 2048) >> 4), idesc_o, accumulate || (k != 0));
         }
       };
       mbar_wait(q_full, 0);
@@ -167,6 +179,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tcgen05_kernel(const
     const float sl2 = P.sl2;
     float m_run = -INFINITY;  // running (possibly stale) row max of raw scores
     float l_run = 0.f;
+    // The two tiles' softmax warps share the SM's MUFU unit.  A ping-pong pair of named barriers lets only one tile
+    // be in its exp2 phase at a time, which keeps the tiles in anti-phase: while tile g exponentiates, the tensor
+    // core runs the other tile's P.V and next Q.K^T.
+    if (PINGPONG && g == 1) named_bar_arrive(1, 256);  // tile 0 goes first
 
     for (int j = 0; j < P.nkv; ++j) {
       mbar_wait(&s_full[g], j & 1);
@@ -195,7 +211,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tcgen05_kernel(const
       if (__any_sync(0xffffffffu, need)) {
         float factor = 1.0f;
         if (need) {
-          factor = exp2f((m_run - m_new) * sl2);  // 0 on the first block
+          factor = ex2_approx((m_run - m_new) * sl2);  // 0 on the first block
           m_run = m_new;
           l_run *= factor;
         }
@@ -213,19 +229,21 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tcgen05_kernel(const
       }
       const float mb = m_run * sl2;
       float lsum = 0.f;
+      if (PINGPONG) named_bar_sync(1 + g, 256);  // wait for this tile's turn on the MUFU
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          float p0 = exp2f(fmaf(__uint_as_float(s[c * 32 + 2 * i]), sl2, -mb));
-          float p1 = exp2f(fmaf(__uint_as_float(s[c * 32 + 2 * i + 1]), sl2, -mb));
+          float p0 = ex2_approx(fmaf(__uint_as_float(s[c * 32 + 2 * i]), sl2, -mb));
+          float p1 = ex2_approx(fmaf(__uint_as_float(s[c * 32 + 2 * i + 1]), sl2, -mb));
           lsum += p0 + p1;
           pk[i] = pack_bf16(p0, p1);
         }
         tmem_st16(tS + c * 16, pk);
       }
       l_run += lsum;
+      if (PINGPONG) named_bar_arrive(2 - g, 256);  // hand the MUFU to the other tile
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(&p_ready[g]);

@@ -30,6 +30,25 @@ FB_DEVICE uint32_t elect_one() {
 // round-to-nearest-even f32 -> bf16 -> f32; the reference rounds to bf16 after every tensor op
 FB_DEVICE float rbf(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
+// single-instruction 2^x (MUFU.EX2); exp2f() without fast-math wraps it in a denormal-range fix-up (3 extra instrs)
+FB_DEVICE float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// 2^x on the FMA/ALU pipes (Cody-Waite split + degree-3 minimax on [-0.5, 0.5], max rel. error 1.0e-4 — below the
+// bf16 rounding applied to the result); x is clamped to >= -126 (results below 2^-126 flush like ex2.approx.ftz)
+FB_DEVICE float ex2_poly(float x) {
+  x = fmaxf(x, -126.0f);
+  const float t = x + 12582912.0f;  // 1.5 * 2^23: the integer part lands in the low mantissa bits
+  const float f = x - (t - 12582912.0f);
+  float p = fmaf(0.055922036f, f, 0.242640083f);
+  p = fmaf(p, f, 0.693121034f);
+  p = fmaf(p, f, 0.999924481f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
 FB_DEVICE uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
@@ -286,6 +305,9 @@ FB_DEVICE void umma_ss_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, ui
       : "memory");
 }
 
+FB_DEVICE void named_bar_arrive(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 FB_DEVICE void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
