@@ -1,6 +1,9 @@
 // fluxb200 — error plumbing, device queries and TMA tensor-map encoding.
 #include <cudaTypedefs.h>
 
+#include <string.h>
+#include <stdlib.h>
+
 #include <mutex>
 #include <vector>
 
@@ -52,6 +55,19 @@ ProfScope::~ProfScope() {
   if (slot < 0) return;
   std::lock_guard<std::mutex> lk(g_prof_mu);
   cudaEventRecord(g_prof_recs[slot].b, stream);
+}
+
+static int g_flag_qkrope = 1, g_flag_pair = -1;
+int get_flag(const char* name) {
+  if (!strcmp(name, "qkrope_fusion")) return g_flag_qkrope;
+  if (!strcmp(name, "gemm_pair")) {
+    if (g_flag_pair < 0) {
+      const char* e = getenv("FLUXB200_GEMM_SINGLE_CTA");
+      g_flag_pair = (e && e[0] == '1') ? 0 : 1;
+    }
+    return g_flag_pair;
+  }
+  return 0;
 }
 
 int num_sms() {
@@ -138,6 +154,12 @@ int encode_tmap_4d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1,
 
 // ---- C ABI: profiling / accounting ----
 extern "C" {
+int fluxb200_set_flag(const char* name, int value) {
+  if (!name) return fb::fail("set_flag: null name");
+  if (!strcmp(name, "qkrope_fusion")) { fb::g_flag_qkrope = value ? 1 : 0; return 0; }
+  if (!strcmp(name, "gemm_pair")) { fb::g_flag_pair = value ? 1 : 0; return 0; }
+  return fb::fail(std::string("set_flag: unknown flag ") + name);
+}
 void fluxb200_profile_enable(int on) {
   std::lock_guard<std::mutex> lk(fb::g_prof_mu);
   fb::g_prof_on = on != 0;

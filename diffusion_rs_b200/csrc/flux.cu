@@ -30,7 +30,7 @@ __constant__ float c_inv_freq[64];
 __constant__ int c_freq_axis[64];
 
 __global__ void pe_table_kernel(const bf16* __restrict__ ids, int rows_per_batch, int batch, int L, int l_off,
-                                bf16* __restrict__ pe_cos, bf16* __restrict__ pe_sin) {
+                                bf16* __restrict__ pe_cos, bf16* __restrict__ pe_sin, uint2* __restrict__ pe2) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= batch * rows_per_batch * 64) return;
   const int f = i & 63;
@@ -39,8 +39,12 @@ __global__ void pe_table_kernel(const bf16* __restrict__ ids, int rows_per_batch
   const float pos = __bfloat162float(ids[static_cast<long long>(row) * 3 + c_freq_axis[f]]);
   const float fr = __bfloat162float(__float2bfloat16_rn(pos * c_inv_freq[f]));
   const long long o = (static_cast<long long>(b) * L + l_off + r) * 64 + f;
-  pe_cos[o] = __float2bfloat16_rn(cosf(fr));
-  pe_sin[o] = __float2bfloat16_rn(sinf(fr));
+  const bf16 c = __float2bfloat16_rn(cosf(fr)), sn = __float2bfloat16_rn(sinf(fr));
+  pe_cos[o] = c;
+  pe_sin[o] = sn;
+  // packed form for the fused GEMM epilogue: {(cos, sin), (-sin, cos)}, laid out [batch][pair][token]
+  const uint32_t cu = __bfloat16_as_ushort(c), su = __bfloat16_as_ushort(sn);
+  pe2[(static_cast<long long>(b) * 64 + f) * L + l_off + r] = make_uint2(cu | (su << 16), (su ^ 0x8000u) | (cu << 16));
 }
 
 static float host_rbf(float x) {
@@ -117,6 +121,7 @@ struct SingleBlock {
 };
 
 struct Workspace {
+  uint2* pe2;
   bf16 *pe_cos, *pe_sin, *temb, *gemb, *e1, *e2, *e3, *e4, *vec, *svec, *mod_all;
   bf16 *img, *txt, *x, *xm, *qkv, *Q, *K, *V, *attn_img, *attn_txt, *big, *pred, *txt_cache;
   float* tvals;
@@ -350,6 +355,9 @@ static GemmDesc gemm_for(const FusedLinear& fl, const bf16* w, const bf16* a, in
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+static void attach_qkrope(GemmDesc& g, const Workspace& w, const bf16* nq, const bf16* nk, int H, int L, int l_off,
+                          int rows_per_batch, float eps);
+
 static Workspace carve(const fluxb200_model* m, void* base, int B, int l_img, int l_txt) {
   Workspace w{};
   uint8_t* p = static_cast<uint8_t*>(base);
@@ -364,6 +372,7 @@ static Workspace carve(const fluxb200_model* m, void* base, int B, int l_img, in
   w.tvals = static_cast<float*>(take(MAX_STEPS * 16 * 4));  // per step: t[8] | guidance[8]
   w.pe_cos = static_cast<bf16*>(take(Mx * 64 * 2));
   w.pe_sin = static_cast<bf16*>(take(Mx * 64 * 2));
+  w.pe2 = static_cast<uint2*>(take(Mx * 64 * 8));
   w.temb = static_cast<bf16*>(take(static_cast<size_t>(B) * 256 * 2));
   w.gemb = static_cast<bf16*>(take(static_cast<size_t>(B) * 256 * 2));
   w.e1 = static_cast<bf16*>(take(static_cast<size_t>(B) * D * 2));
@@ -388,6 +397,15 @@ static Workspace carve(const fluxb200_model* m, void* base, int B, int l_img, in
   w.txt_cache = static_cast<bf16*>(take(Mt * D * 2));
   w.total = off;
   return w;
+}
+
+static void attach_qkrope(GemmDesc& g, const Workspace& w, const bf16* nq, const bf16* nk, int H, int L, int l_off,
+                          int rows_per_batch, float eps) {
+  g.qkrope = 1;
+  g.qk_wq = nq, g.qk_wk = nk, g.qk_pe2 = w.pe2, g.qk_pe_bstride = static_cast<int64_t>(L) * 64;
+  g.qk_Q = w.Q, g.qk_K = w.K, g.qk_V = w.V;
+  g.qk_H = H, g.qk_L = L, g.qk_loff = l_off, g.qk_eps = eps;
+  g.rows_per_batch = rows_per_batch;
 }
 
 // rank-2 Linear on [B, K] (MlpEmbedder / modulation): matmul -> bf16, + bias -> bf16.  `job` indexes the static
@@ -610,8 +628,8 @@ static int prepare_invariants(fluxb200_model* m, const Workspace& w, const StepI
   {
     const int n1 = B * l_txt * 64, n2 = B * l_img * 64;
     count_launch(KK_MISC, 2);
-    pe_table_kernel<<<(n1 + 255) / 256, 256, 0, st>>>(io.txt_ids, l_txt, B, L, 0, w.pe_cos, w.pe_sin);
-    pe_table_kernel<<<(n2 + 255) / 256, 256, 0, st>>>(io.img_ids, l_img, B, L, l_txt, w.pe_cos, w.pe_sin);
+    pe_table_kernel<<<(n1 + 255) / 256, 256, 0, st>>>(io.txt_ids, l_txt, B, L, 0, w.pe_cos, w.pe_sin, w.pe2);
+    pe_table_kernel<<<(n2 + 255) / 256, 256, 0, st>>>(io.img_ids, l_img, B, L, l_txt, w.pe_cos, w.pe_sin, w.pe2);
     FB_CHECK_CUDA(cudaGetLastError());
   }
   return 0;
@@ -635,6 +653,7 @@ static int forward_core(fluxb200_model* m, const Workspace& w, const StepIO& io,
   const float eps = 1e-6f;
   const float scale = 1.0f / sqrtf(static_cast<float>(HEAD_DIM));
   const long long PE_BS = static_cast<long long>(L) * 64;
+  const bool fuse_qk = get_flag("qkrope_fusion") != 0;
   const int JE = m->mod_njobs;  // embedder jobs follow the modulation jobs in the static table
   int rc = 0;
 #define TRY(x)          \
@@ -706,20 +725,28 @@ static int forward_core(fluxb200_model* m, const Workspace& w, const StepIO& io,
       if (!b.img_qkv.quant) {
         g[0] = gemm_for(b.img_qkv, b.img_qkv.w, xm_img, Mi, qkv_img, 3 * D);
         g[1] = gemm_for(b.txt_qkv, b.txt_qkv.w, xm_txt, Mt, qkv_txt, 3 * D);
+        if (fuse_qk) {
+          attach_qkrope(g[0], w, b.img_nq, b.img_nk, H, L, l_txt, l_img, eps);
+          attach_qkrope(g[1], w, b.txt_nq, b.txt_nk, H, L, 0, l_txt, eps);
+        }
         TRY(launch_gemm(g, 2, st));
       } else {  // one staging buffer: expand and run the two streams back to back
         TRY(weight_operand(m, b.img_qkv, &wi, st));
         g[0] = gemm_for(b.img_qkv, wi, xm_img, Mi, qkv_img, 3 * D);
+        if (fuse_qk) attach_qkrope(g[0], w, b.img_nq, b.img_nk, H, L, l_txt, l_img, eps);
         TRY(launch_gemm(g, 1, st));
         TRY(weight_operand(m, b.txt_qkv, &wt, st));
         g[1] = gemm_for(b.txt_qkv, wt, xm_txt, Mt, qkv_txt, 3 * D);
+        if (fuse_qk) attach_qkrope(g[1], w, b.txt_nq, b.txt_nk, H, L, 0, l_txt, eps);
         TRY(launch_gemm(g + 1, 1, st));
       }
     }
-    TRY(launch_qknorm_rope(qkv_txt, 3 * D, l_txt, B, H, L, 0, b.txt_nq, b.txt_nk, w.pe_cos, w.pe_sin, PE_BS, w.Q, w.K,
-                           w.V, eps, st));
-    TRY(launch_qknorm_rope(qkv_img, 3 * D, l_img, B, H, L, l_txt, b.img_nq, b.img_nk, w.pe_cos, w.pe_sin, PE_BS, w.Q,
-                           w.K, w.V, eps, st));
+    if (!fuse_qk) {
+      TRY(launch_qknorm_rope(qkv_txt, 3 * D, l_txt, B, H, L, 0, b.txt_nq, b.txt_nk, w.pe_cos, w.pe_sin, PE_BS, w.Q,
+                             w.K, w.V, eps, st));
+      TRY(launch_qknorm_rope(qkv_img, 3 * D, l_img, B, H, L, l_txt, b.img_nq, b.img_nk, w.pe_cos, w.pe_sin, PE_BS, w.Q,
+                             w.K, w.V, eps, st));
+    }
     {
       AttnDesc a;
       a.q = w.Q, a.k = w.K, a.v = w.V, a.B = B, a.H = H, a.L = L, a.scale = scale;
@@ -782,9 +809,11 @@ static int forward_core(fluxb200_model* m, const Workspace& w, const StepIO& io,
       GemmDesc g = gemm_for(b.lin1, w1, w.xm, Mx, w.qkv, 3 * D);
       g.n_split = 3 * D;  // q|k|v -> qkv buffer; proj_mlp -> gelu -> [attn | mlp] buffer at column D
       g.out1 = w.big, g.ld1 = CAT, g.col_off1 = D, g.act1 = ACT_GELU;
+      if (fuse_qk) attach_qkrope(g, w, b.nq, b.nk, H, L, 0, L, eps);
       TRY(launch_gemm(&g, 1, st));
     }
-    TRY(launch_qknorm_rope(w.qkv, 3 * D, L, B, H, L, 0, b.nq, b.nk, w.pe_cos, w.pe_sin, PE_BS, w.Q, w.K, w.V, eps, st));
+    if (!fuse_qk)
+      TRY(launch_qknorm_rope(w.qkv, 3 * D, L, B, H, L, 0, b.nq, b.nk, w.pe_cos, w.pe_sin, PE_BS, w.Q, w.K, w.V, eps, st));
     {
       AttnDesc a;
       a.q = w.Q, a.k = w.K, a.v = w.V, a.B = B, a.H = H, a.L = L, a.scale = scale;

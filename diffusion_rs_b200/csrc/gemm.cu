@@ -58,6 +58,13 @@ struct alignas(64) GemmProblemDev {
   long long gate_bstride;
   int rows_per_batch, bias_mode, has_alpha;
   float alpha;
+  // fused QK-norm + RoPE epilogue (EV_QKROPE on segment 0)
+  const bf16 *qk_wq, *qk_wk;
+  const uint2* qk_pe2;
+  long long qk_pe_bstride;
+  bf16 *qk_Q, *qk_K, *qk_V;
+  int qk_H, qk_L, qk_loff;
+  float qk_eps;
 };
 
 struct GemmParams {
@@ -106,7 +113,7 @@ __device__ __forceinline__ float gelu_bf16_steps(float v) {
   return __low2float(r);
 }
 
-enum { EV_PLAIN = 0, EV_GELU = 1, EV_RES = 2, EV_GATE_RES = 3, EV_ALPHA = 4, EV_KINDS = 5 };  // x bias mode (3)
+enum { EV_PLAIN = 0, EV_GELU = 1, EV_RES = 2, EV_GATE_RES = 3, EV_ALPHA = 4, EV_KINDS = 5, EV_QKROPE = 5 };  // x bias mode (3)
 
 // 16 consecutive output columns of one row: acc (fp32, from TMEM) -> bf16, fully unrolled, compile-time variant.
 template <int BIAS, int EV>
@@ -163,6 +170,81 @@ __device__ __noinline__ void epi_slow(const uint32_t* acc, int ncols, bf16* outp
     if (ev == EV_GATE_RES || ev == EV_RES) v = rbf(__bfloat162float(resp[e]) + v);
     outp[e] = __float2bfloat16_rn(v);
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused q|k|v epilogue: one thread owns one token row x one head (128 accumulator columns in TMEM).
+//   x = bf16(acc + bias);  q,k: y = bf16(bf16(x / sqrt(mean(x^2) + eps)) * w);  RoPE on interleaved pairs:
+//   out0 = bf16(bf16(c*y0) + bf16(-s*y1)), out1 = bf16(bf16(s*y0) + bf16(c*y1));  v: copied.  Written to [B,H,L,128].
+// Same rounding points as qknorm_rope_kernel (elementwise.cu) / the reference (model.rs:86-95, layer_norm.rs:136-153).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void epi_qkrope(const GemmProblemDev& p, uint32_t t_half, int n_half0, long long grow,
+                                           bool valid) {
+  const int D = p.qk_H * 128;
+  const int which = n_half0 / D;  // 0 q, 1 k, 2 v
+  const int h = (n_half0 - which * D) >> 7;
+  uint32_t x[64];  // the head's 128 values, packed bf16x2
+  float ss = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {  // 16 columns at a time keeps the live register set small
+    uint32_t a[16];
+    tmem_ld16(t_half + c * 16, a);
+    tc_wait_ld();
+    uint4 b0 = make_uint4(0, 0, 0, 0), b1 = b0;
+    if (p.bias_mode != BIAS_NONE) {
+      const uint4* bp = reinterpret_cast<const uint4*>(p.bias + n_half0 + c * 16);
+      b0 = bp[0], b1 = bp[1];
+    }
+    const uint32_t b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float a0 = __uint_as_float(a[2 * i]), a1 = __uint_as_float(a[2 * i + 1]);
+      bf162 v;
+      if (p.bias_mode == BIAS_FUSED) {
+        v = __floats2bfloat162_rn(a0 + bf_lo(b[i]), a1 + bf_hi(b[i]));
+      } else {
+        v = __floats2bfloat162_rn(a0, a1);
+        if (p.bias_mode == BIAS_AFTER_ROUND) v = __hadd2(v, as_bf162(b[i]));
+      }
+      x[c * 8 + i] = as_u32(v);
+      const float2 f = __bfloat1622float2(v);
+      ss = fmaf(f.x, f.x, ss);
+      ss = fmaf(f.y, f.y, ss);
+    }
+  }
+  if (!valid) return;
+  const long long b_idx = p.rows_per_batch > 0 ? grow / p.rows_per_batch : 0;
+  const int l = p.qk_loff + static_cast<int>(grow - b_idx * p.rows_per_batch);
+  bf16* dst = (which == 0 ? p.qk_Q : (which == 1 ? p.qk_K : p.qk_V)) + ((b_idx * p.qk_H + h) * p.qk_L + l) * 128;
+  if (which < 2) {
+    const float denom = sqrtf(ss / 128.0f + p.qk_eps);
+    const float inv = 1.0f / denom;
+    const uint4* wp = reinterpret_cast<const uint4*>(which == 0 ? p.qk_wq : p.qk_wk);
+    // pe2 is laid out [batch][pair][token]: the 32 lanes of a warp (consecutive tokens) read 256 contiguous bytes
+    const uint2* pe = p.qk_pe2 + b_idx * p.qk_pe_bstride + l;
+#pragma unroll
+    for (int i4 = 0; i4 < 16; ++i4) {
+      const uint4 w4 = wp[i4];  // 4 pairs of norm weights
+      const uint32_t wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int i = i4 * 4 + e;
+        const float2 f = __bfloat1622float2(as_bf162(x[i]));
+        // x / denom, correctly rounded via one Newton step on the reciprocal estimate (3 FMAs instead of a div.rn)
+        float q0 = f.x * inv, q1 = f.y * inv;
+        q0 = fmaf(fmaf(-q0, denom, f.x), inv, q0);
+        q1 = fmaf(fmaf(-q1, denom, f.y), inv, q1);
+        const bf162 y = __hmul2(__floats2bfloat162_rn(q0, q1), as_bf162(wv[e]));
+        const uint32_t yu = as_u32(y);
+        const uint32_t y00 = __byte_perm(yu, yu, 0x1010), y11 = __byte_perm(yu, yu, 0x3232);
+        const uint2 cs = pe[static_cast<long long>(i) * p.qk_L];  // cs.x = (cos, sin), cs.y = (-sin, cos)
+        x[i] = as_u32(__hadd2(__hmul2(as_bf162(cs.x), as_bf162(y00)), __hmul2(as_bf162(cs.y), as_bf162(y11))));
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+    reinterpret_cast<uint4*>(dst)[i] = make_uint4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
 }
 
 struct TileCoord {
@@ -359,7 +441,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + acc * BLOCK_N + chalf * 128 + (static_cast<uint32_t>(q * 32) << 16);
-
+      const int n_half0 = tc.n_t * BLOCK_N + chalf * 128;
+      const bool half_seg1 = (p.n_split > 0) && (n_half0 >= p.n_split);
+      if (p.ev0 == EV_QKROPE && !half_seg1 && n_half0 < p.N) {
+        epi_qkrope(p, t_row, n_half0, grow, valid);
+      } else
 #pragma unroll 1
       for (int chunk = 0; chunk < 4; ++chunk) {
         const int n0 = tc.n_t * BLOCK_N + chalf * 128 + chunk * 32;
@@ -431,10 +517,9 @@ int launch_gemm(const GemmDesc* descs, int count, cudaStream_t stream) {
                                        static_cast<int>(GemmCfg<false>::SMEM)));
     FB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(GemmCfg<true>::SMEM)));
-    const char* e = getenv("FLUXB200_GEMM_SINGLE_CTA");  // A/B switch: 1 -> cta_group::1 kernel
-    use_pair = !(e && e[0] == '1');
     attr_set = true;
   }
+  use_pair = get_flag("gemm_pair") != 0;  // A/B switch (env FLUXB200_GEMM_SINGLE_CTA=1 or fluxb200_set_flag)
   const int b_box_rows = use_pair ? GemmCfg<true>::B_ROWS : GemmCfg<false>::B_ROWS;
   GemmParams P;
   memset(&P, 0, sizeof(P));
@@ -443,7 +528,7 @@ int launch_gemm(const GemmDesc* descs, int count, cudaStream_t stream) {
   for (int i = 0; i < count; ++i) {
     const GemmDesc& d = descs[i];
     GemmProblemDev& p = P.p[i];
-    FB_REQUIRE(d.a && d.w && d.out0, "launch_gemm: null operand");
+    FB_REQUIRE(d.a && d.w && (d.out0 || d.qkrope), "launch_gemm: null operand");
     FB_REQUIRE(d.M > 0 && d.N > 0 && d.K > 0, "launch_gemm: empty problem");
     FB_REQUIRE((reinterpret_cast<uintptr_t>(d.a) & 15) == 0 && (reinterpret_cast<uintptr_t>(d.w) & 15) == 0,
                "launch_gemm: operands must be 16-byte aligned (TMA)");
@@ -494,6 +579,18 @@ int launch_gemm(const GemmDesc* descs, int count, cudaStream_t stream) {
       FB_REQUIRE(!(d.act0 == ACT_GELU && (d.res || has_alpha)), "launch_gemm: GELU cannot be combined with residual/alpha");
       FB_REQUIRE(!(has_alpha && d.res), "launch_gemm: alpha cannot be combined with a residual");
       p.ev0 = d.act0 == ACT_GELU ? EV_GELU : (d.gate ? EV_GATE_RES : (d.res ? EV_RES : (has_alpha ? EV_ALPHA : EV_PLAIN)));
+      if (d.qkrope) {
+        FB_REQUIRE(p.ev0 == EV_PLAIN, "launch_gemm: qkrope cannot be combined with another epilogue on segment 0");
+        const int nq = 3 * d.qk_H * 128;
+        FB_REQUIRE(d.qk_H > 0 && (d.n_split == nq || (d.n_split == 0 && d.N == nq)),
+                   "launch_gemm: qkrope needs the q|k|v projection (3*H*128 columns) as segment 0");
+        FB_REQUIRE(d.qk_wq && d.qk_wk && d.qk_pe2 && d.qk_Q && d.qk_K && d.qk_V && d.rows_per_batch > 0,
+                   "launch_gemm: qkrope operands missing");
+        p.ev0 = EV_QKROPE;
+        p.qk_wq = d.qk_wq, p.qk_wk = d.qk_wk, p.qk_pe2 = d.qk_pe2, p.qk_pe_bstride = d.qk_pe_bstride;
+        p.qk_Q = d.qk_Q, p.qk_K = d.qk_K, p.qk_V = d.qk_V;
+        p.qk_H = d.qk_H, p.qk_L = d.qk_L, p.qk_loff = d.qk_loff, p.qk_eps = d.qk_eps;
+      }
       p.ev1 = d.act1 == ACT_GELU ? EV_GELU : EV_PLAIN;
       if (p.ev0 == EV_GATE_RES || p.ev0 == EV_RES) {
         FB_REQUIRE((reinterpret_cast<uintptr_t>(d.res) & 15) == 0 && d.ld0 % 8 == 0, "launch_gemm: residual alignment");

@@ -82,7 +82,19 @@ struct GemmDesc {
   int64_t gate_bstride = 0;
   int rows_per_batch = 0;
   const bf16* res = nullptr;  // same ld as out0; may alias out0; may be used without gate (plain residual add)
+  // Fused QK RMS-norm + RoPE + head-major relayout for columns [0, 3*qk_H*128) (the q|k|v projection): instead of
+  // out0 the epilogue writes Q, K, V [B, H, L, 128] directly (SelfAttention::qkv + apply_rope, model.rs:86-95, 399-427).
+  // Row r belongs to batch r / rows_per_batch and token qk_loff + r % rows_per_batch.
+  int qkrope = 0;
+  const bf16 *qk_wq = nullptr, *qk_wk = nullptr;  // RMS-norm weights [128]
+  const uint2* qk_pe2 = nullptr;                  // [batch][pair 0..63][token]: {(cos, sin), (-sin, cos)} as 2 x bf16x2
+  int64_t qk_pe_bstride = 0;                      // in uint2 elements
+  bf16 *qk_Q = nullptr, *qk_K = nullptr, *qk_V = nullptr;
+  int qk_H = 0, qk_L = 0, qk_loff = 0;
+  float qk_eps = 1e-6f;
 };
+// runtime switches (A/B testing): "qkrope_fusion" (default 1), "gemm_pair" (default 1)
+int get_flag(const char* name);
 // One persistent launch over up to 4 problems (grouped): img + txt streams share the machine.
 int launch_gemm(const GemmDesc* descs, int count, cudaStream_t stream);
 

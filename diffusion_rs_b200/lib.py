@@ -61,6 +61,7 @@ SIGNATURES = {
                                               C.c_uint64, c_void_p]),
     "fluxb200_conv2d_nhwc": (c_int, [c_void_p] * 5 + [c_int] * 6 + [c_void_p]),
     "fluxb200_repack_conv_weight": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "fluxb200_set_flag": (c_int, [C.c_char_p, c_int]),
     "fluxb200_profile_enable": (None, [c_int]),
     "fluxb200_profile_kinds": (c_int, []),
     "fluxb200_profile_kind_name": (C.c_char_p, [c_int]),

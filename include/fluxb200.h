@@ -204,6 +204,9 @@ int fluxb200_groupnorm_nhwc(const void* x, const void* weight, const void* bias,
  * only tracing spans, models/flux/model.rs:240-453).  Timing is off by default and costs two event records per
  * launch when enabled.
  * ---------------------------------------------------------------------------------------------- */
+/* Runtime switches for A/B testing: "qkrope_fusion" (QK-norm + RoPE fused into the q|k|v GEMM epilogue, default 1),
+ * "gemm_pair" (cta_group::2 GEMM, default 1). */
+int fluxb200_set_flag(const char* name, int value);
 void fluxb200_profile_enable(int on);
 int fluxb200_profile_kinds(void);
 const char* fluxb200_profile_kind_name(int kind);

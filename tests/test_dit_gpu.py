@@ -121,3 +121,26 @@ def test_denoise_loop_vs_oracle(fluxlib, small):
     e = _rel(x, xr)
     print(f"\ndenoise 3 steps: rel err {e:.3e}")
     assert e < 3e-2
+
+
+def test_qkrope_fusion_matches_unfused(fluxlib, small):
+    """The fused QK-norm+RoPE GEMM epilogue keeps the rounding points of the stand-alone kernel: outputs agree up to
+    rare one-ulp flips from the different summation order inside the RMS statistic."""
+    from diffusion_rs_b200 import lib as L
+    cfg, weights = small
+    model = _gpu_model(cfg, weights)
+    B, h2, w2, l_txt = 2, 10, 12, 72
+    img, txt, y, ids = _inputs(B, h2, w2, l_txt, cfg, seed=21)
+    t = torch.full((B,), 0.5)
+    gd = torch.full((B,), 3.5)
+    ids_b = ids.to(torch.bfloat16)
+    img_ids = ids_b[l_txt:][None].repeat(B, 1, 1).contiguous().cuda()
+    txt_ids = ids_b[:l_txt][None].repeat(B, 1, 1).contiguous().cuda()
+    outs = []
+    for flag in (1, 0):
+        L.check(fluxlib.fluxb200_set_flag(b"qkrope_fusion", flag))
+        outs.append(model.forward(img.cuda(), img_ids, txt.cuda(), txt_ids, t, y.cuda(), gd).float().cpu())
+    L.check(fluxlib.fluxb200_set_flag(b"qkrope_fusion", 1))
+    rel = ((outs[0] - outs[1]).norm() / outs[1].norm()).item()
+    print(f"\nfused vs unfused qk-norm/rope: rel diff {rel:.3e}, exact {(outs[0] == outs[1]).float().mean():.4f}")
+    assert rel < 1.5e-2
