@@ -170,10 +170,23 @@ class Pipeline:
             raise L.Fluxb200Error("the B200 hot path computes in bf16 (ModelDType::Auto resolves to BF16 on sm_100)")
         if offloading is not None:
             raise L.Fluxb200Error("Offloading::Full is pointless with 180 GB of HBM and is not implemented")
+        bcast = broadcast_weight  # NCCL broadcast of weights at load only (north_star / SURVEY §8(e))
         if source.kind in ("model_id", "dduf"):
-            raise L.Fluxb200Error(
-                f"ModelSource::{source.kind} needs hub/DDUF ingest (SURVEY §8(f) rank 1, not built yet); pass "
-                "ModelSource.tensors(...) with the checkpoint tensors or ModelSource.synthetic(...)")
+            # FileLoader::from_model_source (model_source.rs:97-145): a local snapshot directory or a .dduf archive
+            from . import ingest
+            loader = ingest.open_source(source.kind, source.model_id)
+            tj, tr_tensors, vj, va_tensors, sj = ingest.load_flux_components(loader)
+            fcfg, vcfg, sched = (ingest.flux_config_from_json(tj), ingest.vae_config_from_json(vj),
+                                 ingest.scheduler_config_from_json(sj))
+            tr, va = FluxTransformer(fcfg), AutoEncoderKl(vcfg)
+            for name, t in tr_tensors.items():
+                tr.load_weight(name, bcast(t.cuda()))
+            for name, t in va_tensors.items():
+                va.load_weight(name, bcast(t.cuda()))
+            tr.finalize()
+            va.finalize()
+            torch.cuda.synchronize()
+            return cls(tr, va, sched, fcfg.guidance_embeds)
         is_dev = "schnell" not in source.model_id.lower()
         fcfg = FluxConfig(guidance_embeds=is_dev)
         if source.num_layers is not None:
@@ -182,7 +195,6 @@ class Pipeline:
             fcfg.num_single_layers = source.num_single_layers
         vcfg = VaeConfig()
         sched = SchedulerConfig(use_dynamic_shifting=is_dev, shift=3.0 if is_dev else 1.0)
-        bcast = broadcast_weight  # NCCL broadcast of weights at load only (north_star / SURVEY §8(e))
 
         tr = FluxTransformer(fcfg)
         va = AutoEncoderKl(vcfg)

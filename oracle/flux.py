@@ -161,10 +161,23 @@ def timestep_embedding(t: torch.Tensor, dim: int, mode: Mode):
     return rb(torch.cat([torch.cos(args), torch.sin(args)], -1), mode)
 
 
+class _WidenOnAccess:
+    def __init__(self, weights, device):
+        self._w, self._device = weights, device
+
+    def __getitem__(self, k):
+        return self._w[k].to(device=self._device, dtype=torch.float32)
+
+    def __contains__(self, k):
+        return k in self._w
+
+
 class FluxOracle:
     def __init__(self, cfg: FluxConfig, weights: dict[str, torch.Tensor], mode: Mode = O.REF, device="cpu"):
         self.cfg, self.mode, self.device = cfg, mode, device
-        self.w = {k: v.to(device=device, dtype=torch.float32) for k, v in weights.items()}
+        # weights stay in their storage dtype (bf16) and are widened on access, so a full-depth model (23.8 GB bf16)
+        # does not need a second 48 GB f32 copy
+        self.w = _WidenOnAccess(weights, device)
 
     # Linear on a rank-3 activation with bias: cuBLASLt fused bias (unquantized/mod.rs:52-66)
     def lin3(self, x, name):

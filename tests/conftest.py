@@ -11,6 +11,7 @@ if str(ROOT) not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: test needs a real B200 (run with -m gpu under gpurun)")
+    config.addinivalue_line("markers", "slow: full-depth parity run (minutes of CPU oracle time)")
 
 
 @pytest.fixture(scope="session")

@@ -144,3 +144,47 @@ def test_qkrope_fusion_matches_unfused(fluxlib, small):
     rel = ((outs[0] - outs[1]).norm() / outs[1].norm()).item()
     print(f"\nfused vs unfused qk-norm/rope: rel diff {rel:.3e}, exact {(outs[0] == outs[1]).float().mean():.4f}")
     assert rel < 1.5e-2
+
+
+@pytest.mark.slow
+def test_c1_schnell_256_full_depth_single_step(fluxlib):
+    """BASELINE config C1: FLUX.1-schnell (no guidance embed), 256x256, ONE DiT step at full depth (19 + 38 blocks),
+    CPU oracle (reference semantics) vs the B200 path.  L = 256 img + 256 txt tokens."""
+    cfg = OF.FluxConfig(guidance_embeds=False)  # 19 double + 38 single blocks
+    weights = OF.make_weights(cfg)
+    model = _gpu_model(cfg, weights)
+    B, h2, w2, l_txt = 1, 16, 16, 256
+    img, txt, y, ids = _inputs(B, h2, w2, l_txt, cfg)
+    t = torch.full((B,), 1.0)
+    ids_b = ids.to(torch.bfloat16)
+    out = model.forward(img.cuda(), ids_b[l_txt:][None].contiguous().cuda(), txt.cuda(),
+                        ids_b[:l_txt][None].contiguous().cuda(), t, y.cuda(), None)
+    torch.cuda.synchronize()
+    ref = OF.FluxOracle(cfg, weights, O.REF).forward(img.float(), ids, txt.float(), t, y.float(), None)
+    tru = OF.FluxOracle(cfg, weights, O.F32).forward(img.float(), ids, txt.float(), t, y.float(), None)
+    e1, e2, e3 = _rel(out, ref), _rel(out, tru), _rel(ref, tru)
+    print(f"\nC1 schnell 256^2 full depth: |ours-ref|={e1:.3e} |ours-f32|={e2:.3e} |ref-f32|={e3:.3e}")
+    assert e1 < 6e-2
+    assert e2 < 1.5 * e3 + 2e-3
+
+
+def test_dit_step_720x1280_geometry(fluxlib):
+    """BASELINE config C4 geometry (90x160 latent -> 3600 image tokens + 512 text tokens = 4112, none of which is a
+    multiple of the 128/256-row tiles) at reduced depth: exercises the M tails of the CTA-pair GEMM, the fused
+    QK-norm/RoPE epilogue on ragged tiles and the masked last KV block of the attention kernel."""
+    cfg = OF.FluxConfig(num_layers=1, num_single_layers=1, guidance_embeds=True)
+    weights = OF.make_weights(cfg)
+    model = _gpu_model(cfg, weights)
+    B, h2, w2, l_txt = 1, 45, 80, 512
+    img, txt, y, ids = _inputs(B, h2, w2, l_txt, cfg, seed=99)
+    t = torch.full((B,), 0.3)
+    gd = torch.full((B,), 3.5)
+    ids_b = ids.to(torch.bfloat16)
+    out = model.forward(img.cuda(), ids_b[l_txt:][None].contiguous().cuda(), txt.cuda(),
+                        ids_b[:l_txt][None].contiguous().cuda(), t, y.cuda(), gd)
+    torch.cuda.synchronize()
+    ref = OF.FluxOracle(cfg, weights, O.REF).forward(img.float(), ids, txt.float(), t, y.float(), gd)
+    e = _rel(out, ref)
+    print(f"\n720x1280 geometry (L=4112), 1+1 blocks: |ours-ref|={e:.3e}")
+    assert torch.isfinite(out.float()).all()
+    assert e < 2e-2
