@@ -28,6 +28,28 @@ int fluxb200_linear(const void* a, int64_t lda, const void* w, int64_t ldw, cons
   return launch_gemm(&d, 1, static_cast<cudaStream_t>(stream));
 }
 
+int fluxb200_linear_quant(const void* a, int64_t lda, const void* packed, const void* aux, int32_t kind,
+                          int32_t blocksize, const void* bias, void* out, int64_t ldo, int32_t M, int32_t N, int32_t K,
+                          int32_t bias_mode, int32_t act, fluxb200_stream_t stream) {
+  FB_REQUIRE(kind >= QB_NF4 && kind <= QB_INT8, "linear_quant: kind must be 1 (nf4), 2 (fp4), 3 (q4_k) or 4 (int8)");
+  FB_REQUIRE(N % 128 == 0, "linear_quant: N must be a multiple of 128");
+  QuantB qb;
+  qb.count = 1;
+  qb.m[0].packed = static_cast<const uint8_t*>(packed);
+  qb.m[0].absmax = (kind == QB_NF4 || kind == QB_FP4) ? static_cast<const float*>(aux) : nullptr;
+  qb.m[0].scb = kind == QB_INT8 ? static_cast<const float*>(aux) : nullptr;
+  qb.m[0].row_begin = 0, qb.m[0].kind = kind, qb.m[0].blocksize = blocksize > 0 ? blocksize : 64;
+  GemmDesc d;
+  d.a = static_cast<const bf16*>(a), d.lda = lda;
+  d.qb = &qb;
+  d.M = M, d.N = N, d.K = K;
+  d.out0 = static_cast<bf16*>(out), d.ld0 = ldo;
+  d.bias = static_cast<const bf16*>(bias);
+  d.bias_mode = bias ? bias_mode : BIAS_NONE;
+  d.act0 = act;
+  return launch_gemm(&d, 1, static_cast<cudaStream_t>(stream));
+}
+
 int fluxb200_sdpa(const void* q, const void* k, const void* v, void* out, int32_t B, int32_t H, int32_t L,
                   float scale, fluxb200_stream_t stream) {
   AttnDesc d;

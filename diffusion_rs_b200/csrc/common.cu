@@ -57,9 +57,10 @@ ProfScope::~ProfScope() {
   cudaEventRecord(g_prof_recs[slot].b, stream);
 }
 
-static int g_flag_qkrope = 1, g_flag_pair = -1;
+static int g_flag_qkrope = 1, g_flag_pair = -1, g_flag_fdq = 0;
 int get_flag(const char* name) {
   if (!strcmp(name, "qkrope_fusion")) return g_flag_qkrope;
+  if (!strcmp(name, "fused_dequant")) return g_flag_fdq;
   if (!strcmp(name, "gemm_pair")) {
     if (g_flag_pair < 0) {
       const char* e = getenv("FLUXB200_GEMM_SINGLE_CTA");
@@ -127,6 +128,24 @@ static int encode_nd(CUtensorMap* out, const void* base, int rank, const uint64_
   return 0;
 }
 
+int encode_tmap_2d_raw(CUtensorMap* out, const void* base, int elem_bytes, uint64_t inner, uint64_t outer,
+                       uint64_t outer_stride_bytes, uint32_t box_inner, uint32_t box_outer) {
+  auto enc = get_encode();
+  if (!enc) return fail("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+  cuuint64_t gdim[2] = {inner, outer};
+  cuuint64_t gstr[1] = {outer_stride_bytes};
+  cuuint32_t bdim[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapDataType dt = elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8;
+  CUresult r = enc(out, dt, 2, const_cast<void*>(base), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail("cuTensorMapEncodeTiled (raw) failed, CUresult=" + std::to_string(static_cast<int>(r)) + " inner=" +
+                std::to_string(inner) + " outer=" + std::to_string(outer) + " stride=" +
+                std::to_string(outer_stride_bytes) + " box=" + std::to_string(box_inner) + "x" + std::to_string(box_outer));
+  return 0;
+}
+
 int encode_tmap_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t outer_stride_bytes,
                    uint32_t box_inner, uint32_t box_outer) {
   uint64_t dims[2] = {inner, outer};
@@ -158,6 +177,7 @@ int fluxb200_set_flag(const char* name, int value) {
   if (!name) return fb::fail("set_flag: null name");
   if (!strcmp(name, "qkrope_fusion")) { fb::g_flag_qkrope = value ? 1 : 0; return 0; }
   if (!strcmp(name, "gemm_pair")) { fb::g_flag_pair = value ? 1 : 0; return 0; }
+  if (!strcmp(name, "fused_dequant")) { fb::g_flag_fdq = value ? 1 : 0; return 0; }
   return fb::fail(std::string("set_flag: unknown flag ") + name);
 }
 void fluxb200_profile_enable(int on) {

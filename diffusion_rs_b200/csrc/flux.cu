@@ -109,6 +109,7 @@ struct FusedLinear {
   bool quant = false;
   int bias_mode3 = BIAS_FUSED;  // rank-3 call sites: cuBLASLt fused bias (dense) vs separate add (bnb)
   std::vector<Member> members;
+  QuantB qb;  // quantised: operand description for the fused-dequant GEMM producer
 };
 
 struct DoubleBlock {
@@ -298,6 +299,14 @@ static int build_linear(fluxb200_model* m, FusedLinear& fl, const std::vector<st
     m->wscratch_elems = std::max(m->wscratch_elems, static_cast<size_t>(fl.N) * K);
     // bnb: separate bf16 add after the matmul (bitsandbytes/mod.rs:301-312); gguf: f32 result + bias, one rounding
     fl.bias_mode3 = (fl.members[0].q == Q_Q4K) ? BIAS_FUSED : BIAS_AFTER_ROUND;
+    FB_REQUIRE(fl.members.size() <= 4, "at most 4 fused quantised members");
+    fl.qb.count = static_cast<int>(fl.members.size());
+    for (size_t i = 0; i < fl.members.size(); ++i) {
+      const Member& mb = fl.members[i];
+      QuantMember& qm = fl.qb.m[i];
+      qm.packed = mb.packed, qm.absmax = mb.absmax, qm.scb = mb.scb, qm.row_begin = mb.row_off, qm.blocksize = mb.blocksize;
+      qm.kind = mb.q == Q_NF4 ? QB_NF4 : (mb.q == Q_FP4 ? QB_FP4 : (mb.q == Q_Q4K ? QB_Q4K : QB_INT8));
+    }
   }
   return 0;
 }
@@ -315,9 +324,14 @@ static void drop_raw_dense(fluxb200_model* m, const FusedLinear& fl) {
 }
 
 // Weight operand for the GEMM: dense pointer, or expand the quantised members into the staging buffer.
-static int weight_operand(fluxb200_model* m, const FusedLinear& fl, const bf16** w, cudaStream_t st) {
+static int weight_operand(fluxb200_model* m, const FusedLinear& fl, const bf16** w, cudaStream_t st,
+                          bool for_gemm = true) {
   if (!fl.quant) {
     *w = fl.w;
+    return 0;
+  }
+  if (for_gemm && get_flag("fused_dequant") && fl.N % 128 == 0 && fl.K % 64 == 0) {
+    *w = nullptr;  // gemm_for() switches to the fused-dequant producer
     return 0;
   }
   for (auto& mb : fl.members) {
@@ -344,9 +358,12 @@ static int weight_operand(fluxb200_model* m, const FusedLinear& fl, const bf16**
   return 0;
 }
 
+// Dense: W read by TMA.  Quantised: the GEMM's producer warps expand the packed weights on the fly (fb::QuantB),
+// unless fused de-quantisation is switched off ("fused_dequant" = 0), in which case `w` is the staging buffer.
 static GemmDesc gemm_for(const FusedLinear& fl, const bf16* w, const bf16* a, int M, bf16* out, int64_t ldo) {
   GemmDesc d;
   d.a = a, d.lda = fl.K, d.w = w, d.ldb = fl.K;
+  if (fl.quant && w == nullptr) d.qb = &fl.qb;
   d.M = M, d.N = fl.N, d.K = fl.K;
   d.out0 = out, d.ld0 = ldo;
   d.bias = fl.bias, d.bias_mode = fl.bias_mode3;
@@ -413,7 +430,7 @@ static void attach_qkrope(GemmDesc& g, const Workspace& w, const bf16* nq, const
 static int small_linear(fluxb200_model* m, const FusedLinear& fl, int job, int row_base, const bf16* x, bf16* out_base,
                         int B, cudaStream_t st) {
   const bf16* w = nullptr;
-  if (int rc = weight_operand(m, fl, &w, st)) return rc;  // quantised: expands into the staging buffer
+  if (int rc = weight_operand(m, fl, &w, st, /*for_gemm=*/false)) return rc;  // quantised: expands into the staging buffer
   return launch_gemv_jobs(m->mod_jobs_dev + job, 1, row_base, fl.N, x, fl.K, B, fl.K, out_base, st);
 }
 

@@ -17,6 +17,8 @@
 #include <vector>
 
 #include "internal.h"
+#include <cuda_fp16.h>
+
 #include "ptx.cuh"
 
 namespace fb {
@@ -27,16 +29,22 @@ static constexpr int BLOCK_K = 64;
 static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
 // CTA2 = a CTA pair (cta_group::2) computes one 256x256 tile: each CTA stages its own 128 rows of A and HALF of the
 // 256 W rows, the MMA (M=256, issued by the leader) reads both halves -> 1.5x less L2->SM traffic per FLOP.
-template <bool CTA2>
+// QB = quantised B: every stage additionally holds the PACKED weights of the k-block (TMA-staged, <= 8 KB), which
+// the dequant-producer warps expand into the stage's bf16 B tile.
+static constexpr int PK_BYTES = 8192;
+static constexpr int PK_AUX_OFF = 4096;  // second TMA box of a stage (absmax / Q4_K header) lands here
+template <bool CTA2, bool QB = false>
 struct GemmCfg {
   static constexpr int B_ROWS = CTA2 ? BLOCK_N / 2 : BLOCK_N;
   static constexpr int B_BYTES = B_ROWS * BLOCK_K * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;  // 32 KB (pair) / 48 KB (single)
-  static constexpr int STAGES = CTA2 ? 6 : 4;
-  static constexpr size_t SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES + (QB ? PK_BYTES : 0);  // 32 (+8) KB (pair) / 48 KB (single)
+  static constexpr int STAGES = QB ? 5 : (CTA2 ? 6 : 4);
+  static constexpr size_t SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 4096 /*code-pair LUTs*/;
 };
-static constexpr int GEMM_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
-static constexpr int EPI_WARPS = 8;
+static constexpr int GEMM_THREADS = 320;  // warp 0 TMA, warp 1 MMA, then epilogue (+ dequant producer) warps
+// dense B (TMA):      warps 2..9 = 8 epilogue warps
+// quantised B (QB=1): warps 2..5 = 4 epilogue warps, warps 6..9 = 4 dequant-producer warps (one W row per thread)
+template <bool QB> struct EpiCfg { static constexpr int WARPS = QB ? 4 : 8; };
 static constexpr int MAX_PROBLEMS = 4;
 static constexpr int GROUP_M = 8;
 static constexpr int CONV_TH = 8, CONV_TW = 16;  // 8x16 output pixels = one 128-row M tile
@@ -59,6 +67,12 @@ struct alignas(64) GemmProblemDev {
   long long gate_bstride;
   int rows_per_batch, bias_mode, has_alpha;
   float alpha;
+  // quantised B operand (fused dequant producer): per member a map over the packed bytes and one over the
+  // auxiliary data (bnb: f32 absmax; Q4_K: the 16-byte block headers)
+  CUtensorMap tmap_pk[4];
+  CUtensorMap tmap_aux[4];
+  QuantMember qm[4];
+  int qcount;
   // fused QK-norm + RoPE epilogue (EV_QKROPE on segment 0)
   const bf16 *qk_wq, *qk_wk;
   const uint2* qk_pe2;
@@ -271,9 +285,177 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& P, int t) {
   return c;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fused de-quantisation producer.  Thread `row` owns row `row` of this CTA's B tile (128 rows in pair mode): per
+// k-block it reads that row's 64 packed weights from HBM, expands them with the reference's arithmetic
+//   NF4/FP4 : bf16(code[nibble] * absmax[block])           (kernels/bitsandbytes/dequant.cu:94-170)
+//   Q4_K    : bf16(f16(d*sc*q - dmin*m))                    (k_quants.rs:1568-1599, gguf/mod.rs:29-31)
+//   int8    : bf16(float(w) * SCB[row] / 127)               (dequant.cu:205-214)
+// and writes the 128-byte row into the K-major 128B-swizzled smem tile the MMA consumes (chunk c of row r lives at
+// r*128 + ((c ^ (r & 7)) << 4)), then fence.proxy.async + one mbarrier arrival per warp.
+// ------------------------------------------------------------------------------------------------
+__constant__ float c_nf4[16] = {-1.0f, -0.6961928009986877f, -0.5250730514526367f, -0.39491748809814453f,
+                                -0.28444138169288635f, -0.18477343022823334f, -0.09105003625154495f, 0.0f,
+                                0.07958029955625534f, 0.16093020141124725f, 0.24611230194568634f, 0.33791524171829224f,
+                                0.44070982933044434f, 0.5626170039176941f, 0.7229568362236023f, 1.0f};
+__constant__ float c_fp4[16] = {0.0f,  5.208333333e-03f,  0.66666667f,  1.0f,  0.33333333f,  0.5f,  0.16666667f,  0.25f,
+                                -0.0f, -5.208333333e-03f, -0.66666667f, -1.0f, -0.33333333f, -0.5f, -0.16666667f, -0.25f};
+
+// packed data of one k-block (64 weights) of one W row, per format
+template <int KIND> struct DqRegs;
+template <> struct DqRegs<QB_NF4> { uint4 a, b; float am; };          // 32 nibble bytes + absmax (also FP4)
+template <> struct DqRegs<QB_Q4K> { uint4 hdr, a, b; };                // d, dmin, 12 scale bytes + 32 q bytes
+template <> struct DqRegs<QB_INT8> { uint4 a, b, c, d; };              // 64 int8
+
+// read this thread's row of the stage's TMA-staged packed data (shared memory, conflict-free 16-byte reads)
+template <int KIND>
+__device__ __forceinline__ void dq_read(const uint8_t* pk, int row, DqRegs<KIND>& r, int aux_sel) {
+  if constexpr (KIND == QB_NF4) {
+    const uint4* src = reinterpret_cast<const uint4*>(pk + row * 32);
+    r.a = src[0], r.b = src[1];
+    r.am = *reinterpret_cast<const float*>(pk + PK_AUX_OFF + row * 16 + aux_sel * 4);  // aligned group of 4 absmax
+  } else if constexpr (KIND == QB_Q4K) {
+    const uint4* src = reinterpret_cast<const uint4*>(pk + row * 32);
+    r.a = src[0], r.b = src[1];
+    r.hdr = *reinterpret_cast<const uint4*>(pk + PK_AUX_OFF + row * 16);
+  } else {
+    const uint4* src = reinterpret_cast<const uint4*>(pk + row * 64);
+    r.a = src[0], r.b = src[1], r.c = src[2], r.d = src[3];
+  }
+}
+
+// expand one k-block of one row to 64 bf16 (32 packed words)
+template <int KIND>
+__device__ __forceinline__ void dq_decode(const DqRegs<KIND>& r, uint32_t* o, const float2* lut, int j, float row_scale) {
+  if constexpr (KIND == QB_NF4) {
+    const uint32_t w[8] = {r.a.x, r.a.y, r.a.z, r.a.w, r.b.x, r.b.y, r.b.z, r.b.w};
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float2 cp = lut[(w[i >> 2] >> (8 * (i & 3))) & 0xffu];
+      o[i] = pack_bf16(cp.x * r.am, cp.y * r.am);
+    }
+  } else if constexpr (KIND == QB_Q4K) {
+    const __half2 dm = *reinterpret_cast<const __half2*>(&r.hdr.x);
+    const float d = __low2float(dm), dmin = __high2float(dm);
+    // 12 scale bytes = hdr.y, hdr.z, hdr.w
+    auto sbyte = [&](int idx) -> uint32_t {
+      const uint32_t word = idx < 4 ? r.hdr.y : (idx < 8 ? r.hdr.z : r.hdr.w);
+      return (word >> (8 * (idx & 3))) & 0xffu;
+    };
+    float dd[2], mm[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int is = 2 * j + h;
+      uint32_t s6, m6;
+      if (is < 4) {
+        s6 = sbyte(is) & 63, m6 = sbyte(is + 4) & 63;
+      } else {
+        s6 = (sbyte(is + 4) & 0xF) | ((sbyte(is - 4) >> 6) << 4);
+        m6 = (sbyte(is + 4) >> 4) | ((sbyte(is) >> 6) << 4);
+      }
+      dd[h] = __fmul_rn(d, static_cast<float>(s6));
+      mm[h] = __fmul_rn(dmin, static_cast<float>(m6));
+    }
+    const uint32_t w[8] = {r.a.x, r.a.y, r.a.z, r.a.w, r.b.x, r.b.y, r.b.z, r.b.w};
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {  // bytes 2i, 2i+1: low nibbles -> elements 2i, 2i+1; high nibbles -> 32 + 2i, 33 + 2i
+      const uint32_t b0 = (w[i >> 1] >> (16 * (i & 1))) & 0xffu, b1 = (w[i >> 1] >> (16 * (i & 1) + 8)) & 0xffu;
+      const float l0 = __half2float(__float2half_rn(__fsub_rn(__fmul_rn(dd[0], static_cast<float>(b0 & 15)), mm[0])));
+      const float l1 = __half2float(__float2half_rn(__fsub_rn(__fmul_rn(dd[0], static_cast<float>(b1 & 15)), mm[0])));
+      const float h0 = __half2float(__float2half_rn(__fsub_rn(__fmul_rn(dd[1], static_cast<float>(b0 >> 4)), mm[1])));
+      const float h1 = __half2float(__float2half_rn(__fsub_rn(__fmul_rn(dd[1], static_cast<float>(b1 >> 4)), mm[1])));
+      o[i] = pack_bf16(l0, l1);
+      o[16 + i] = pack_bf16(h0, h1);
+    }
+  } else {
+    const uint32_t w[16] = {r.a.x, r.a.y, r.a.z, r.a.w, r.b.x, r.b.y, r.b.z, r.b.w,
+                            r.c.x, r.c.y, r.c.z, r.c.w, r.d.x, r.d.y, r.d.z, r.d.w};
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int v0 = static_cast<int8_t>((w[i >> 1] >> (16 * (i & 1))) & 0xffu);
+      const int v1 = static_cast<int8_t>((w[i >> 1] >> (16 * (i & 1) + 8)) & 0xffu);
+      o[i] = pack_bf16((static_cast<float>(v0) * row_scale) / 127.f, (static_cast<float>(v1) * row_scale) / 127.f);
+    }
+  }
+}
+
+// all k-blocks of one tile for one row, format fixed at compile time.  The packed bytes arrive in the stage's PK
+// area by TMA (issued by warp 0 together with the A tile), so these threads never have a global load in flight when
+// they execute fence.proxy.async (which would otherwise drain it and serialise every k-block on HBM latency).
+template <bool CTA2, int KIND>
+__device__ __forceinline__ void dq_tile(const QuantMember& qm, bool in_range, int num_kb, int n_local, uint8_t* smem,
+                                        uint64_t* full_bar, uint64_t* pk_full, int row, const float2* lut2, int STAGES,
+                                        int STAGE_BYTES, int& stage, uint32_t& phase) {
+  const int lane = threadIdx.x & 31;
+  const float2* lut = lut2 + (qm.kind == QB_FP4 ? 256 : 0);
+  const float row_scale = (KIND == QB_INT8 && in_range) ? __ldg(qm.scb + n_local) : 0.f;
+  const int bs_shift = 31 - __clz(qm.blocksize);  // blocksizes are powers of two (bitsandbytes/mod.rs:14)
+  for (int kb = 0; kb < num_kb; ++kb) {
+    uint8_t* sa = smem + stage * STAGE_BYTES;
+    uint8_t* sb = sa + A_BYTES + row * 128;
+    const uint8_t* pk = sa + STAGE_BYTES - PK_BYTES;
+    // pk_full completes only after the TMA producer has seen empty_bar[stage]: the B tile slot is free as well
+    mbar_wait(&pk_full[stage], phase);
+    DqRegs<KIND> r;
+    dq_read<KIND>(pk, row, r, ((kb * BLOCK_K) >> bs_shift) & 3);
+    uint32_t o[32];  // 64 bf16
+    dq_decode<KIND>(r, o, lut, kb & 3, row_scale);
+    const int sw = row & 7;
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      *reinterpret_cast<uint4*>(sb + ((c ^ sw) << 4)) = make_uint4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+    fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+    __syncwarp();
+    if (lane == 0) {
+      if (CTA2) mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(&full_bar[stage]), 0));
+      else      mbar_arrive(&full_bar[stage]);
+    }
+    if (++stage == STAGES) {
+      stage = 0;
+      phase ^= 1;
+    }
+  }
+}
+
 template <bool CTA2>
+__device__ __forceinline__ void dequant_producer(const GemmParams& P, uint8_t* smem, uint64_t* full_bar,
+                                                 uint64_t* pk_full, int unit_id, int num_units, uint32_t cta_rank,
+                                                 int row, const float2* lut2, int STAGES, int STAGE_BYTES, int B_ROWS) {
+  int stage = 0;
+  uint32_t phase = 0;
+  for (int t = unit_id; t < P.total_tiles; t += num_units) {
+    TileCoord tc = decode_tile(P, t);
+    const GemmProblemDev& p = P.p[tc.prob];
+    const int n = tc.n_t * BLOCK_N + (CTA2 ? static_cast<int>(cta_rank) * B_ROWS : 0) + row;  // row of W
+    const bool in_range = n < p.N;
+    int mi = 0;
+#pragma unroll
+    for (int i = 1; i < 4; ++i)
+      if (i < p.qcount && n >= p.qm[i].row_begin) mi = i;
+    const QuantMember& qm = p.qm[mi];
+    const int n_local = n - qm.row_begin;
+    switch (qm.kind) {  // uniform across the CTA: a tile never straddles two members
+      case QB_Q4K:
+        dq_tile<CTA2, QB_Q4K>(qm, in_range, p.num_kb, n_local, smem, full_bar, pk_full, row, lut2, STAGES, STAGE_BYTES,
+                              stage, phase);
+        break;
+      case QB_INT8:
+        dq_tile<CTA2, QB_INT8>(qm, in_range, p.num_kb, n_local, smem, full_bar, pk_full, row, lut2, STAGES, STAGE_BYTES,
+                               stage, phase);
+        break;
+      default:
+        dq_tile<CTA2, QB_NF4>(qm, in_range, p.num_kb, n_local, smem, full_bar, pk_full, row, lut2, STAGES, STAGE_BYTES,
+                              stage, phase);
+        break;
+    }
+  }
+}
+
+template <bool CTA2, bool QB>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams P) {
-  using Cfg = GemmCfg<CTA2>;
+  using Cfg = GemmCfg<CTA2, QB>;
+  constexpr int EPI_WARPS = EpiCfg<QB>::WARPS;
+  constexpr int DQ_WARPS = QB ? 4 : 0;  // arrivals on a full barrier: 1 (TMA expect_tx) + dequant warps (of both CTAs)
   constexpr int STAGES = Cfg::STAGES;
   constexpr int STAGE_BYTES = Cfg::STAGE_BYTES;
   const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0;       // rank inside the CTA pair
@@ -286,7 +468,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;  // [2]
   uint64_t* tmem_empty = tmem_full + 2;      // [2]
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* pk_full = tmem_empty + 2;        // [STAGES] packed weights of the stage have landed (QB only)
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(pk_full + STAGES);
+  float2* lut2 = reinterpret_cast<float2*>(smem + STAGES * STAGE_BYTES + 256);  // [2][256] byte -> (hi, lo) code pairs
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -297,8 +481,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       tma_prefetch_desc(&P.p[i].tmap_b);
     }
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], 1 + (CTA2 ? 2 : 1) * DQ_WARPS);
       mbar_init(&empty_bar[s], 1);
+      mbar_init(&pk_full[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
@@ -308,6 +493,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   }
   if (warp == 1) {
     if (CTA2) tmem_alloc_2sm(tmem_base_slot, 512); else tmem_alloc(tmem_base_slot, 512);
+  }
+  if (QB) {
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) {
+      const int b = i & 255;
+      const float* cb = (i < 256) ? c_nf4 : c_fp4;
+      lut2[i] = make_float2(cb[b >> 4], cb[b & 15]);  // high nibble is the first weight (dequant.cu:155-156)
+    }
   }
   tc_fence_before();
   if (CTA2) cluster_sync_all(); else __syncthreads();  // peer barriers must be initialised before remote arrivals
@@ -348,18 +540,42 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
           } else {
             a_c0 = b_c0 = kb * BLOCK_K;
           }
+          if (QB) {
+            // packed weights of this CTA's B rows for this k-block -> the stage's PK area (local barrier)
+            int mi = 0;
+#pragma unroll
+            for (int i = 1; i < 4; ++i)
+              if (i < p.qcount && b_row0 >= p.qm[i].row_begin) mi = i;
+            const int kind = p.qm[mi].kind;
+            const int r0 = b_row0 - p.qm[mi].row_begin;
+            uint8_t* pk = sb + Cfg::B_BYTES;
+            if (kind == QB_INT8) {
+              mbar_arrive_expect_tx(&pk_full[stage], Cfg::B_ROWS * 64);
+              tma_load_2d(pk, &p.tmap_pk[mi], &pk_full[stage], kb * 64, r0);
+            } else if (kind == QB_Q4K) {
+              mbar_arrive_expect_tx(&pk_full[stage], Cfg::B_ROWS * 48);
+              tma_load_2d(pk, &p.tmap_pk[mi], &pk_full[stage], (kb >> 2) * 144 + 16 + (kb & 3) * 32, r0);
+              tma_load_2d(pk + PK_AUX_OFF, &p.tmap_aux[mi], &pk_full[stage], (kb >> 2) * 144, r0);
+            } else {
+              const int bs_shift = 31 - __clz(p.qm[mi].blocksize);
+              mbar_arrive_expect_tx(&pk_full[stage], Cfg::B_ROWS * 48);
+              tma_load_2d(pk, &p.tmap_pk[mi], &pk_full[stage], kb * 32, r0);
+              // TMA box starts must be 16-byte aligned: fetch the aligned group of 4 absmax values, the consumer picks
+              tma_load_2d(pk + PK_AUX_OFF, &p.tmap_aux[mi], &pk_full[stage], (((kb * BLOCK_K) >> bs_shift) & ~3) * 4, r0);
+            }
+          }
           if (CTA2) {
             // both CTAs' bytes are credited to the leader's barrier; only the leader arms it
             const uint32_t bar = mapa_u32(smem_u32(&full_bar[stage]), 0);
-            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (QB ? A_BYTES : STAGE_BYTES));
             if (p.conv) tma_load_4d_2sm(sa, &p.tmap_a, bar, a_c0, cw0 + kw - pad, ch0 + kh - pad, cn);
             else        tma_load_2d_2sm(sa, &p.tmap_a, bar, a_c0, m_t * BLOCK_M);
-            tma_load_2d_2sm(sb, &p.tmap_b, bar, b_c0, b_row0);
+            if (!QB) tma_load_2d_2sm(sb, &p.tmap_b, bar, b_c0, b_row0);
           } else {
-            mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+            mbar_arrive_expect_tx(&full_bar[stage], QB ? A_BYTES : STAGE_BYTES);
             if (p.conv) tma_load_4d(sa, &p.tmap_a, &full_bar[stage], a_c0, cw0 + kw - pad, ch0 + kh - pad, cn);
             else        tma_load_2d(sa, &p.tmap_a, &full_bar[stage], a_c0, m_t * BLOCK_M);
-            tma_load_2d(sb, &p.tmap_b, &full_bar[stage], b_c0, b_row0);
+            if (!QB) tma_load_2d(sb, &p.tmap_b, &full_bar[stage], b_c0, b_row0);
           }
           if (++stage == STAGES) {
             stage = 0;
@@ -379,11 +595,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       for (int t = unit_id; t < P.total_tiles; t += num_units) {
         TileCoord tc = decode_tile(P, t);
         const GemmProblemDev& p = P.p[tc.prob];
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        if (CTA2) mbar_wait_cluster(&tmem_empty[acc], acc_phase ^ 1); else mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
         for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+          if (CTA2) mbar_wait_cluster(&full_bar[stage], phase); else mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
           const uint64_t da = umma_smem_desc_sw128(sa, 16, 1024);
@@ -409,10 +625,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
         }
       }
     }
+  } else if (QB && warp >= 2 + EPI_WARPS) {
+    // ================= dequant producer warps (quantised B): one W row per thread, 64 weights per k-block =========
+    dequant_producer<CTA2>(P, smem, full_bar, pk_full, unit_id, num_units, cta_rank, (warp - 2 - EPI_WARPS) * 32 + lane,
+                           lut2, STAGES, STAGE_BYTES, Cfg::B_ROWS);
   } else {
-    // ================= epilogue warps (2..9) =================
+    // ================= epilogue warps =================
     const int q = warp & 3;              // TMEM lane quarter this warp may access (hardware: warp_id % 4)
-    const int chalf = (warp - 2) >> 2;   // which 128-column half of the tile this warp drains
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = unit_id; t < P.total_tiles; t += num_units) {
@@ -441,6 +660,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
+      // 8 epilogue warps: each drains one 128-column half; 4 epilogue warps (quantised-B kernel): both halves in turn
+#pragma unroll 1
+      for (int hh = 0; hh < (EPI_WARPS == 4 ? 2 : 1); ++hh) {
+      const int chalf = EPI_WARPS == 4 ? hh : ((warp - 2) >> 2);
       const uint32_t t_row = tmem_base + acc * BLOCK_N + chalf * 128 + (static_cast<uint32_t>(q * 32) << 16);
       const int n_half0 = tc.n_t * BLOCK_N + chalf * 128;
       const bool half_seg1 = (p.n_split > 0) && (n_half0 >= p.n_split);
@@ -484,6 +707,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
           epi_slow(acc_r, p.N - n0, outp, biasp, bias_mode, ev, gatep, resp, p.alpha);
         }
       }
+      }  // hh
       // release the accumulator back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -511,16 +735,26 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
 // ------------------------------------------------------------------------------------------------
 int launch_gemm(const GemmDesc* descs, int count, cudaStream_t stream) {
   FB_REQUIRE(count >= 1 && count <= MAX_PROBLEMS, "launch_gemm: 1..4 problems per launch");
+  static_assert(sizeof(GemmParams) < 32000, "kernel parameter block too large");
   static bool attr_set = false;
   static bool use_pair = true;
   if (!attr_set) {
-    FB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    FB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(GemmCfg<false>::SMEM)));
-    FB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    FB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(GemmCfg<true>::SMEM)));
+    FB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(GemmCfg<true, true>::SMEM)));
     attr_set = true;
   }
   use_pair = get_flag("gemm_pair") != 0;  // A/B switch (env FLUXB200_GEMM_SINGLE_CTA=1 or fluxb200_set_flag)
+  bool quant_b = false;
+  for (int i = 0; i < count; ++i) quant_b |= (descs[i].qb != nullptr);
+  if (quant_b) {
+    for (int i = 0; i < count; ++i)
+      FB_REQUIRE(descs[i].qb != nullptr && !descs[i].conv, "launch_gemm: quantised and dense problems cannot share a launch");
+    use_pair = true;  // the fused-dequant producer exists for the CTA-pair kernel only
+  }
   const int b_box_rows = use_pair ? GemmCfg<true>::B_ROWS : GemmCfg<false>::B_ROWS;
   GemmParams P;
   memset(&P, 0, sizeof(P));
@@ -529,10 +763,45 @@ int launch_gemm(const GemmDesc* descs, int count, cudaStream_t stream) {
   for (int i = 0; i < count; ++i) {
     const GemmDesc& d = descs[i];
     GemmProblemDev& p = P.p[i];
-    FB_REQUIRE(d.a && d.w && (d.out0 || d.qkrope), "launch_gemm: null operand");
+    FB_REQUIRE(d.a && (d.w || d.qb) && (d.out0 || d.qkrope), "launch_gemm: null operand");
     FB_REQUIRE(d.M > 0 && d.N > 0 && d.K > 0, "launch_gemm: empty problem");
     FB_REQUIRE((reinterpret_cast<uintptr_t>(d.a) & 15) == 0 && (reinterpret_cast<uintptr_t>(d.w) & 15) == 0,
                "launch_gemm: operands must be 16-byte aligned (TMA)");
+    p.qcount = 0;
+    if (d.qb) {
+      FB_REQUIRE(d.qb->count >= 1 && d.qb->count <= 4, "launch_gemm: 1..4 quantised members");
+      FB_REQUIRE(d.K % 64 == 0, "launch_gemm: quantised B needs K % 64 == 0");
+      p.qcount = d.qb->count;
+      for (int qi = 0; qi < d.qb->count; ++qi) {
+        const QuantMember& qmem = d.qb->m[qi];
+        FB_REQUIRE(qmem.packed && (reinterpret_cast<uintptr_t>(qmem.packed) & 15) == 0, "launch_gemm: packed weights must be 16-byte aligned");
+        FB_REQUIRE(qmem.row_begin % 128 == 0, "launch_gemm: quantised members must start on a multiple of 128 rows");
+        if (qmem.kind == QB_NF4 || qmem.kind == QB_FP4)
+          FB_REQUIRE(qmem.absmax && qmem.blocksize % 64 == 0, "launch_gemm: 4-bit members need absmax and blocksize % 64 == 0");
+        if (qmem.kind == QB_Q4K) FB_REQUIRE(d.K % 256 == 0, "launch_gemm: Q4_K needs K % 256 == 0");
+        if (qmem.kind == QB_INT8) FB_REQUIRE(qmem.scb != nullptr, "launch_gemm: int8 members need SCB");
+        p.qm[qi] = qmem;
+        // tensor maps over this member's packed bytes (+ aux): rows = the member's output rows
+        const uint64_t rows = static_cast<uint64_t>((qi + 1 < d.qb->count ? d.qb->m[qi + 1].row_begin : d.N) - qmem.row_begin);
+        int rc = 0;
+        if (qmem.kind == QB_INT8) {
+          rc = encode_tmap_2d_raw(&p.tmap_pk[qi], qmem.packed, 1, d.K, rows, d.K, 64, 128);
+        } else if (qmem.kind == QB_Q4K) {
+          const uint64_t rb = static_cast<uint64_t>(d.K / 256) * 144;
+          rc = encode_tmap_2d_raw(&p.tmap_pk[qi], qmem.packed, 1, rb, rows, rb, 32, 128);
+          if (!rc) rc = encode_tmap_2d_raw(&p.tmap_aux[qi], qmem.packed, 1, rb, rows, rb, 16, 128);
+        } else {
+          const uint64_t nabs = static_cast<uint64_t>(d.K / qmem.blocksize);
+          FB_REQUIRE(d.K % qmem.blocksize == 0 && (nabs * 4) % 16 == 0 && nabs >= 4,
+                     "launch_gemm: fused 4-bit dequant needs (K / blocksize) % 4 == 0 (TMA row pitch of absmax)");
+          FB_REQUIRE((reinterpret_cast<uintptr_t>(qmem.absmax) & 15) == 0, "launch_gemm: absmax must be 16-byte aligned");
+          rc = encode_tmap_2d_raw(&p.tmap_pk[qi], qmem.packed, 1, d.K / 2, rows, d.K / 2, 32, 128);
+          // absmax is mapped as raw bytes (an f32-typed map with a 4-element box faults on sm_100): 16-byte boxes
+          if (!rc) rc = encode_tmap_2d_raw(&p.tmap_aux[qi], qmem.absmax, 1, nabs * 4, rows, nabs * 4, 16, 128);
+        }
+        if (rc) return rc;
+      }
+    }
     FB_REQUIRE((reinterpret_cast<uintptr_t>(d.out0) & 15) == 0 || (d.N % 8) != 0,
                "launch_gemm: output must be 16-byte aligned");
     FB_REQUIRE(d.n_split % BLOCK_N == 0, "launch_gemm: n_split must be a multiple of 256");
@@ -562,8 +831,8 @@ int launch_gemm(const GemmDesc* descs, int count, cudaStream_t stream) {
       int rc = encode_tmap_2d(&p.tmap_a, d.a, d.K, d.M, static_cast<uint64_t>(d.lda) * 2, BLOCK_K, BLOCK_M);
       if (rc) return rc;
     }
-    FB_REQUIRE(d.ldb % 8 == 0, "launch_gemm: ldb must be a multiple of 8");
-    {
+    if (!d.qb) {
+      FB_REQUIRE(d.ldb % 8 == 0, "launch_gemm: ldb must be a multiple of 8");
       int rc = encode_tmap_2d(&p.tmap_b, d.w, d.K, d.N, static_cast<uint64_t>(d.ldb) * 2, BLOCK_K, b_box_rows);
       if (rc) return rc;
     }
@@ -627,16 +896,17 @@ int launch_gemm(const GemmDesc* descs, int count, cudaStream_t stream) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * std::min(tile, num_sms() / 2));
     cfg.blockDim = dim3(GEMM_THREADS);
-    cfg.dynamicSmemBytes = GemmCfg<true>::SMEM;
+    cfg.dynamicSmemBytes = quant_b ? GemmCfg<true, true>::SMEM : GemmCfg<true, false>::SMEM;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr, cfg.numAttrs = 1;
-    FB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<true>, P));
+    if (quant_b) FB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<true, true>, P));
+    else         FB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<true, false>, P));
   } else {
     const int grid = std::min(tile, num_sms());
-    gemm_tcgen05_kernel<false><<<grid, GEMM_THREADS, GemmCfg<false>::SMEM, stream>>>(P);
+    gemm_tcgen05_kernel<false, false><<<grid, GEMM_THREADS, GemmCfg<false>::SMEM, stream>>>(P);
   }
   FB_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -39,6 +39,10 @@ int encode_tmap_4d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1,
                    uint64_t stride1_bytes, uint64_t stride2_bytes, uint64_t stride3_bytes, uint32_t b0, uint32_t b1,
                    uint32_t b2, uint32_t b3);
 
+// un-swizzled 2-D map over raw bytes / f32 (packed quantised weights and their scales)
+int encode_tmap_2d_raw(CUtensorMap* out, const void* base, int elem_bytes, uint64_t inner, uint64_t outer,
+                       uint64_t outer_stride_bytes, uint32_t box_inner, uint32_t box_outer);
+
 int num_sms();
 
 // ---- launch accounting + optional per-kernel-class CUDA-event timing (bench.py roofline evidence) ----
@@ -56,12 +60,15 @@ struct ProfScope {  // records an event pair around the launches issued in its l
 enum { ACT_NONE = 0, ACT_GELU = 1 };
 enum { BIAS_NONE = 0, BIAS_FUSED = 1, BIAS_AFTER_ROUND = 2 };
 
+struct QuantB;
+
 struct GemmDesc {
   // operands (bf16, row-major, K contiguous). lda/ldb in elements.
   const bf16* a = nullptr;
   int64_t lda = 0;
   const bf16* w = nullptr;
   int64_t ldb = 0;
+  const QuantB* qb = nullptr;  // non-null: W is quantised and expanded inside the GEMM (w is ignored)
   int M = 0, N = 0, K = 0;
   // implicit-GEMM 3x3/1x1 convolution: A is an NHWC image [cN, cH, cW, cC]; M = cN*cH*cW output pixels,
   // K = taps*cC with W laid out [N, taps, cC]; ksize in {1,3}, padding = ksize/2, stride 1.
@@ -93,6 +100,22 @@ struct GemmDesc {
   int qk_H = 0, qk_L = 0, qk_loff = 0;
   float qk_eps = 1e-6f;
 };
+// Quantised B operand: the GEMM's producer warps expand packed weights straight into the swizzled smem tile
+// (no bf16 copy of the weight ever exists in HBM).  Up to 4 members = the reference Linears fused along N.
+enum { QB_NF4 = 1, QB_FP4 = 2, QB_Q4K = 3, QB_INT8 = 4 };
+struct QuantMember {
+  const uint8_t* packed = nullptr;  // nibbles / Q4_K blocks / int8 weights of this member, row-major [N_m, K]
+  const float* absmax = nullptr;    // bnb 4-bit: f32 absmax per `blocksize` weights (nested absmax already expanded)
+  const float* scb = nullptr;       // int8: per-row scale
+  int row_begin = 0;                // first output column (row of W) of this member; multiple of 128
+  int kind = 0;
+  int blocksize = 64;
+};
+struct QuantB {
+  QuantMember m[4];
+  int count = 0;
+};
+
 // runtime switches (A/B testing): "qkrope_fusion" (default 1), "gemm_pair" (default 1)
 int get_flag(const char* name);
 // One persistent launch over up to 4 problems (grouped): img + txt streams share the machine.

@@ -85,6 +85,19 @@ FB_DEVICE uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok;
 }
+FB_DEVICE uint32_t mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok;
+}
 // Bounded wait: a pipeline bug must trap, never hang the GPU box.
 FB_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
@@ -93,6 +106,19 @@ FB_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
       printf("fluxb200: mbarrier timeout block=(%d,%d,%d) thread=%d bar=%u parity=%u\n", blockIdx.x, blockIdx.y,
              blockIdx.z, threadIdx.x, smem_u32(bar), parity);
+      __trap();
+    }
+  }
+}
+
+// same, with cluster-scope acquire: pairs with release.cluster arrivals from the peer CTA
+FB_DEVICE void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  long long t0 = clock64();
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("fluxb200: mbarrier (cluster) timeout block=(%d,%d,%d) thread=%d bar=%u parity=%u\n", blockIdx.x,
+             blockIdx.y, blockIdx.z, threadIdx.x, smem_u32(bar), parity);
       __trap();
     }
   }
@@ -256,6 +282,12 @@ FB_DEVICE uint32_t mapa_u32(uint32_t smem_addr, uint32_t rank) {
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
   return r;
+}
+// arrival on a (possibly remote) barrier without a cluster-scope release: for hot loops whose payload is made
+// visible by other means (fence.proxy.async / tcgen05 fences).  A release.cluster arrive drains the thread's
+// outstanding loads and invalidates L1 every time.
+FB_DEVICE void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 FB_DEVICE void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");

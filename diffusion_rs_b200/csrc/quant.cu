@@ -56,10 +56,14 @@ template <typename T, int DATA_TYPE>
 __global__ void __launch_bounds__(256) dequant_4bit_kernel(const uint8_t* __restrict__ A,
                                                            const float* __restrict__ absmax, T* __restrict__ out,
                                                            int half_block, long long n) {
+  // the 16-entry code book goes to shared memory: lanes index it with different nibbles, which a __constant__ bank
+  // would serialise (one address per cycle) — that alone held the first version of this kernel at 0.7 TB/s
+  __shared__ float lut[16];
+  if (threadIdx.x < 16) lut[threadIdx.x] = (DATA_TYPE == 2) ? kNF4[threadIdx.x] : kFP4[threadIdx.x];
+  __syncthreads();
   const long long nbytes = (n + 1) / 2;
   const long long byte0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * 16;
   if (byte0 >= nbytes) return;
-  const float* lut = (DATA_TYPE == 2) ? kNF4 : kFP4;
   const bool fast = (byte0 + 16 <= nbytes) && (2 * (byte0 + 16) <= n) && (half_block % 16 == 0) &&
                     ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
   if (fast) {

@@ -25,6 +25,8 @@ SIGNATURES = {
     "fluxb200_version": (c_int, []),
     "fluxb200_linear": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_int,
                                 c_int, c_int, c_void_p, c_int64, c_int, c_void_p, c_float, c_void_p]),
+    "fluxb200_linear_quant": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int64,
+                                      c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "fluxb200_sdpa": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p]),
     "fluxb200_layernorm_modulate": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int, c_int,
                                             c_float, c_void_p]),

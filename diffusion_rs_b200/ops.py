@@ -41,6 +41,23 @@ def linear(x, w, bias=None, *, bias_mode=BIAS_FUSED, act=ACT_NONE, gate=None, ro
     return out
 
 
+QUANT_KINDS = {"nf4": 1, "fp4": 2, "q4k": 3, "int8": 4}
+
+
+def linear_quant(x, packed, aux, kind: str, N: int, bias=None, *, blocksize=64, bias_mode=BIAS_AFTER_ROUND,
+                 act=ACT_NONE, out=None):
+    """out = epilogue(x @ dequant(packed).T) with the weight expanded inside the GEMM — BnbLinear / GgufMatMul."""
+    _chk_bf16(x, bias)
+    K = x.shape[-1]
+    M = x.numel() // K
+    if out is None:
+        out = torch.empty(*x.shape[:-1], N, device=x.device, dtype=torch.bfloat16)
+    L.check(L.load().fluxb200_linear_quant(L.ptr(x), K, L.ptr(packed), L.ptr(aux), QUANT_KINDS[kind], blocksize,
+                                           L.ptr(bias), L.ptr(out), N, M, N, K,
+                                           bias_mode if bias is not None else BIAS_NONE, act, L.current_stream()))
+    return out
+
+
 def sdpa(q, k, v, scale: float):
     """q,k,v [B,H,L,128] -> [B,L,H*128] — ops::sdpa (ops.rs:247-262) + transpose/flatten (model.rs:101)."""
     _chk_bf16(q, k, v)

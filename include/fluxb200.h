@@ -46,6 +46,15 @@ int fluxb200_linear(const void* a, int64_t lda, const void* w, int64_t ldw, cons
                     int64_t gate_bstride, int32_t rows_per_batch, const void* res, float alpha,
                     fluxb200_stream_t stream);
 
+/* Same as fluxb200_linear with a QUANTISED weight that is expanded inside the GEMM's operand producer (never as a
+ * bf16 tensor in HBM).  kind: 1 = bnb NF4, 2 = bnb FP4 (packed nibbles [N*K/2], aux = f32 absmax per `blocksize`
+ * weights), 3 = GGUF Q4_K (144-byte super-blocks, aux = NULL), 4 = LLM.int8 (int8 [N,K], aux = f32 SCB[N]).
+ * Replaces BnbLinear::forward / GgufMatMul::forward_via_half (bitsandbytes/mod.rs:301-312, gguf/mod.rs:42-49):
+ * W = dequant(packed) rounded to bf16, then the bf16 GEMM.  Needs N % 128 == 0 and K % 64 == 0 (Q4_K: K % 256 == 0). */
+int fluxb200_linear_quant(const void* a, int64_t lda, const void* packed, const void* aux, int32_t kind,
+                          int32_t blocksize, const void* bias, void* out, int64_t ldo, int32_t M, int32_t N, int32_t K,
+                          int32_t bias_mode, int32_t act, fluxb200_stream_t stream);
+
 /* Joint attention. q,k,v: bf16 [B,H,L,128]; out: bf16 [B,L,H*128] (== transpose(1,2).flatten_from(2)).
  * Replaces diffusion_rs_backend::ops::sdpa (ops.rs:247-262) + the casts in model.rs:40-51, softcapping = 1. */
 int fluxb200_sdpa(const void* q, const void* k, const void* v, void* out, int32_t B, int32_t H, int32_t L,
@@ -205,7 +214,9 @@ int fluxb200_groupnorm_nhwc(const void* x, const void* weight, const void* bias,
  * launch when enabled.
  * ---------------------------------------------------------------------------------------------- */
 /* Runtime switches for A/B testing: "qkrope_fusion" (QK-norm + RoPE fused into the q|k|v GEMM epilogue, default 1),
- * "gemm_pair" (cta_group::2 GEMM, default 1). */
+ * "gemm_pair" (cta_group::2 GEMM, default 1), "fused_dequant" (model path: quantised weights expanded inside the GEMM's
+ * operand producer instead of through an L2-sized bf16 staging buffer; default 0 because at M = 4608 tokens per weight
+ * the staged path is faster). */
 int fluxb200_set_flag(const char* name, int value);
 void fluxb200_profile_enable(int on);
 int fluxb200_profile_kinds(void);

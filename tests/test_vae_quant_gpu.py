@@ -182,6 +182,20 @@ def _quantize_model_weights(weights, kind):
             blocks = Q.quantize_q4k(w)
             tensors[name] = ("q4k", torch.from_numpy(blocks.reshape(-1)), (N, K))
             deq[name] = torch.from_numpy(Q.dequant_q4k_bf16(blocks).reshape(N, K)).bfloat16()
+        elif kind == "int8":
+            scb = np.abs(w).max(1).astype(np.float32)
+            w8 = np.rint(w / scb[:, None] * 127.0).clip(-127, 127).astype(np.int8)
+            tensors[name] = torch.from_numpy(w8)
+            tensors[name[:-len("weight")] + "SCB"] = torch.from_numpy(scb)
+            deq[name] = torch.from_numpy(Q.bf16_round(Q.dequant_int8_rowwise(w8, scb))).bfloat16()
+        elif kind == "fp4":
+            packed, absmax = Q.quantize_4bit(w, 64, "fp4")
+            tensors[name] = torch.from_numpy(packed.reshape(-1, 1))
+            tensors[name + ".absmax"] = torch.from_numpy(absmax)  # no double quantisation: f32 absmax
+            tensors[name + ".quant_map"] = torch.from_numpy(Q.FP4_LUT.copy())
+            js = Q.quant_state_json(64, (N, K))
+            tensors[name + ".quant_state.bitsandbytes__fp4"] = torch.from_numpy(np.frombuffer(js, dtype=np.uint8).copy())
+            deq[name] = torch.from_numpy(Q.bf16_round(Q.dequant_4bit(packed, absmax, 64, N * K, "fp4").reshape(N, K))).bfloat16()
         else:
             packed, absmax = Q.quantize_4bit(w, 64, "nf4")
             a8, ncode, nabs, off = Q.quantize_absmax_nested(absmax, 256)
@@ -199,7 +213,7 @@ def _quantize_model_weights(weights, kind):
     return tensors, deq
 
 
-@pytest.mark.parametrize("kind", ["nf4", "q4k"])
+@pytest.mark.parametrize("kind", ["nf4", "fp4", "int8", "q4k"])
 def test_quantised_dit_step(fluxlib, kind):
     """C3 / C5 semantics at reduced depth: oracle weight = dequant(quant(W)); bnb adds the bias after rounding."""
     from diffusion_rs_b200.transformer import DT_Q4K, FluxConfig, FluxTransformer
@@ -222,9 +236,15 @@ def test_quantised_dit_step(fluxlib, kind):
     idb = ids.bfloat16()
     t = torch.tensor([0.6])
     gd = torch.tensor([3.5])
-    out = m.forward(img.cuda(), idb[l_txt:][None].contiguous().cuda(), txt.cuda(), idb[:l_txt][None].contiguous().cuda(), t,
-                    y.cuda(), gd)
+    from diffusion_rs_b200 import lib as L
+    args = (img.cuda(), idb[l_txt:][None].contiguous().cuda(), txt.cuda(), idb[:l_txt][None].contiguous().cuda(), t,
+            y.cuda(), gd)
+    L.check(fluxlib.fluxb200_set_flag(b"fused_dequant", 1))
+    out = m.forward(*args).clone()  # weights expanded inside the GEMM's operand producer
+    L.check(fluxlib.fluxb200_set_flag(b"fused_dequant", 0))
+    out_staged = m.forward(*args).clone()  # same weights expanded into a bf16 staging buffer first (default)
     torch.cuda.synchronize()
+    assert torch.equal(out, out_staged), "fused and staged de-quantisation must feed identical bf16 weights to the MMA"
 
     class QOracle(OF.FluxOracle):
         def lin3(self, x, name):
@@ -241,3 +261,32 @@ def test_quantised_dit_step(fluxlib, kind):
     e = _rel(out, ref)
     print(f"\n{kind} DiT step: rel err {e:.3e}")
     assert e < 3e-2
+
+
+@pytest.mark.parametrize("kind", ["nf4", "fp4", "q4k", "int8"])
+@pytest.mark.parametrize("M,N,K", [(512, 3072, 3072), (200, 384, 1024)])
+def test_linear_quant_equals_dense_on_dequantised_weight(fluxlib, kind, M, N, K):
+    """Fused-dequant GEMM (C ABI fluxb200_linear_quant) == dense GEMM fed with the oracle's dequantised bf16 weight,
+    bit for bit (same bf16 operands, same MMA order)."""
+    from diffusion_rs_b200 import ops
+    rs = np.random.RandomState(7)
+    w = (rs.randn(N, K) / math.sqrt(K)).astype(np.float32)
+    if kind in ("nf4", "fp4"):
+        packed, absmax = Q.quantize_4bit(w, 64, kind)
+        wd = Q.bf16_round(Q.dequant_4bit(packed, absmax, 64, N * K, kind).reshape(N, K))
+        pk, aux = torch.from_numpy(packed).cuda(), torch.from_numpy(absmax).cuda()
+    elif kind == "q4k":
+        blocks = Q.quantize_q4k(w)
+        wd = Q.dequant_q4k_bf16(blocks).reshape(N, K)
+        pk, aux = torch.from_numpy(blocks.reshape(-1)).cuda(), None
+    else:
+        scb = np.abs(w).max(1).astype(np.float32)
+        w8 = np.rint(w / scb[:, None] * 127.0).clip(-127, 127).astype(np.int8)
+        wd = Q.bf16_round(Q.dequant_int8_rowwise(w8, scb))
+        pk, aux = torch.from_numpy(w8).cuda(), torch.from_numpy(scb).cuda()
+    x = torch.randn(M, K, generator=torch.Generator().manual_seed(8)).bfloat16().cuda()
+    b = (0.1 * torch.randn(N, generator=torch.Generator().manual_seed(9))).bfloat16().cuda()
+    y = ops.linear_quant(x, pk, aux, kind, N, b, bias_mode=ops.BIAS_AFTER_ROUND)
+    ref = ops.linear(x, torch.from_numpy(wd).bfloat16().cuda(), b, bias_mode=ops.BIAS_AFTER_ROUND)
+    torch.cuda.synchronize()
+    assert torch.equal(y, ref)
