@@ -189,6 +189,8 @@ def run_ours(args):
     from diffusion_rs_b200.pipeline import (DiffusionGenerationParams, ModelSource, Pipeline, PromptEmbeds,
                                             calculate_shift, latent_hw, make_ids, patchify)
     lib = L.load()
+    if args.attn_variant is not None:  # A/B switch for kernel experiments (scripts/); the default build is variant 0
+        L.check(lib.fluxb200_set_flag(b"attn_variant", args.attn_variant))
     quant = args.quant
     t_load = time.perf_counter()
     pipe = Pipeline.load(ModelSource.synthetic("black-forest-labs/FLUX.1-dev", quant=quant, num_layers=args.layers,
@@ -346,6 +348,7 @@ def main():
     ap.add_argument("--single-layers", type=int, default=None, help="debug: reduced number of single blocks")
     ap.add_argument("--no-kernel-timing", dest="kernel_timing", action="store_false")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--attn-variant", type=int, default=None, help="debug: attention kernel build (see attention.cu)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -4,13 +4,24 @@
 // (diffusion_rs_backend/src/ops.rs:247-262, called from diffusion_rs_core/src/models/flux/model.rs:40-51, 97-102).
 //
 // One CTA = one (batch, head) x 256 query rows (two 128-row tiles that ping-pong on the tensor core):
-//   warp 0       TMA producer: Q0,Q1 once; K_j, V_j through 2-stage rings (128B swizzle)
-//   warp 1       MMA issuer  : S_g = Q_g.K_j^T (SS) and O_g += P_g.V_j (A = P from TMEM, B = V MN-major from smem)
-//   warps 2..5   softmax for tile 0, warps 6..9 softmax for tile 1 (ping-pong on the MUFU unit through a pair of
-//                named barriers): one thread per query row, online softmax in
-//                fp32 with lazy rescaling of the TMEM-resident O accumulator; P is written back to TMEM as bf16
-//                over the S columns it came from.
+//   warps 0..3   softmax for tile 0, warps 4..7 softmax for tile 1 (ping-pong on the MUFU unit through a pair of
+//                named barriers): one thread per query row, online softmax in fp32 with lazy rescaling of the
+//                TMEM-resident O accumulator; P is written back to TMEM as bf16 over the S columns it came from.
+//   warp 8       TMA producer: Q0,Q1 once; K_j, V_j through rings (128B swizzle)
+//   warp 9       MMA issuer  : S_g = Q_g.K_j^T (SS) and O_g += P_g.V_j (A = P from TMEM, B = V MN-major from smem)
 // TMEM: S0 [0,128) S1 [128,256) O0 [256,384) O1 [384,512) fp32 columns.
+//
+// What the measurements of this round say (scripts/attn_variants.py = clock64 trace of CTA 0, scripts/ubench/*.cu):
+//  * per tile the work is a strict chain  S ready -> TMEM load -> row max -> exp2 -> P -> P.V -> next Q.K^T;  the two
+//    tiles fill each other's gaps.  First cut: 3480 clk per 128-row kv block (tensor pipe 52 %).
+//  * tcgen05.mma with M=128 (cta_group::1) issues at best every ~92 clk for any N <= 192 (77 clk when SS and TS MMAs
+//    alternate), i.e. 70-83 % of the tensor peak for the N=128 shapes of attention; the same MMAs for a CTA pair
+//    (M=256) take the 64-clk floor.  The pair build of this kernel (PAIR=true) is correct and its MMAs are faster,
+//    but the cross-CTA P handoff adds ~300 clk of latency to the chain, so it is not (yet) faster end to end.
+//  * the MMA-issuing warp must not lose issue slots to the softmax warps (highest warp id wins arbitration) and
+//    its operands must be uniform (no per-MMA R2UR/ELECT waterfall): 3480 -> 3250 clk.
+//  * the exp2 phase is MUFU-bound (16/clk/SM); a packed f32x2 degree-3 polynomial for every 4th pair: 3250 -> 3030.
+//  * inside the DiT step (power-capped clocks) all of this is worth 844 -> 1006 TFLOP/s.
 #include "internal.h"
 #include "ptx.cuh"
 
@@ -21,9 +32,7 @@ static constexpr int TQ = 128;            // query rows per tile
 static constexpr int TKV = 128;           // kv rows per block
 static constexpr int TILE_BYTES = TQ * HD * 2;   // 32 KB (two 16 KB swizzle-atom columns)
 static constexpr int HALF_BYTES = TILE_BYTES / 2;
-static constexpr int ATT_THREADS = 320;
-static constexpr bool PINGPONG = true;
-static constexpr size_t ATT_SMEM = 6 * TILE_BYTES + 1024 + 256;
+static constexpr int ATT_THREADS = 384;  // warpgroups 0,1: softmax of tile 0,1; warpgroup 2: TMA, MMA, 2 idle warps
 
 struct AttnParams {
   CUtensorMap tmap_q, tmap_k, tmap_v;  // 3D {128, L, B*H}, box {64, 128, 1}
@@ -34,178 +43,389 @@ struct AttnParams {
   bf16* out_a;
   bf16* out_b;
   long long ld_a, ld_b;
+  long long* trace;  // debug: clock64 stamps of CTA 0, [kv block][tile][8]; nullptr in production
 };
 
+// packed f32x2 arithmetic (FFMA2 / FADD2): one issue slot for two lanes of work
+FB_DEVICE void ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
+}
+FB_DEVICE void fadd2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "add.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+FB_DEVICE float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
+// 2^x for two lanes on the FMA pipe (see ex2_poly): 10 instructions per pair, no MUFU
+FB_DEVICE void ex2_poly2(float& y0, float& y1, float x0, float x1) {
+  x0 = fmaxf(x0, -126.0f);
+  x1 = fmaxf(x1, -126.0f);
+  float t0, t1, u0, u1, f0, f1, p0, p1;
+  fadd2(t0, t1, x0, x1, 12582912.0f, 12582912.0f);
+  fadd2(u0, u1, t0, t1, -12582912.0f, -12582912.0f);
+  ffma2(f0, f1, u0, u1, -1.0f, -1.0f, x0, x1);
+  ffma2(p0, p1, f0, f1, 0.055922036f, 0.055922036f, 0.242640083f, 0.242640083f);
+  ffma2(p0, p1, p0, p1, f0, f1, 0.693121034f, 0.693121034f);
+  ffma2(p0, p1, p0, p1, f0, f1, 0.999924481f, 0.999924481f);
+  y0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+  y1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+}
+
+// The softmax of one 128x128 score tile for one thread (= one query row), shared by the single-CTA and CTA-pair
+// kernels.  `s` holds the row's 128 raw scores; P is written back over the first 64 TMEM columns of the tile as bf16
+// pairs, 16 scores (8 packed columns = one k-step of O += P.V) at a time, and published to the MMA thread in NHAND
+// instalments so that most of P.V runs under the remaining exponentials.  The wait for an instalment's TMEM stores
+// is issued one chunk late (after the next chunk's arithmetic), so the MUFU never idles behind tcgen05.wait::st.
+//   POLY_MOD  every POLY_MOD-th PAIR of exponentials is evaluated on the FMA pipe (ex2_poly2) instead of the MUFU
+//             unit (0 = all on MUFU).  Measured (scripts/ubench/exp_rate.cu): a 128x128 tile costs 1600 clk with all
+//             exponentials on the MUFU (16/clk/SM) and 1080 clk with every 4th pair on the FMA pipe.
+//   WITH_MAX  also return the row maximum of the raw scores; the 3-input max instructions run on the ALU pipe under
+//             the MUFU-bound exponentials instead of in a separate 330-clk phase in front of them.
+template <int POLY_MOD, int NHAND, bool WITH_MAX, class Arrive>
+FB_DEVICE void softmax_exp_store(uint32_t (&s)[128], uint32_t tS, float sl2, float nmb, float& l_run, float& bmax,
+                                 int lane, Arrive&& arrive) {
+  constexpr int CH = 8 / NHAND;  // chunks per instalment
+  float ls0 = 0.f, ls1 = 0.f;
+  float bm0 = -INFINITY, bm1 = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    uint32_t pk[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float x0, x1, p0, p1;
+      if (WITH_MAX) {
+        if (i & 1) bm1 = fmax3(bm1, __uint_as_float(s[c * 16 + 2 * i]), __uint_as_float(s[c * 16 + 2 * i + 1]));
+        else       bm0 = fmax3(bm0, __uint_as_float(s[c * 16 + 2 * i]), __uint_as_float(s[c * 16 + 2 * i + 1]));
+      }
+      ffma2(x0, x1, __uint_as_float(s[c * 16 + 2 * i]), __uint_as_float(s[c * 16 + 2 * i + 1]), sl2, sl2, nmb, nmb);
+      if (POLY_MOD > 0 && (i % (POLY_MOD > 0 ? POLY_MOD : 1) == POLY_MOD - 1)) {
+        ex2_poly2(p0, p1, x0, x1);
+      } else {
+        p0 = ex2_approx(x0);
+        p1 = ex2_approx(x1);
+      }
+      fadd2(ls0, ls1, ls0, ls1, p0, p1);
+      pk[i] = pack_bf16(p0, p1);
+    }
+    if (c > 0 && c % CH == 0) {  // chunks [c-CH, c) were stored one chunk's worth of work ago
+      tc_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) arrive(c / CH - 1);
+    }
+    tmem_st8(tS + c * 8, pk);
+  }
+  l_run += ls0 + ls1;
+  if (WITH_MAX) bmax = fmaxf(bm0, bm1);
+}
+
+// One kernel, two launch modes:
+//   PAIR = false  one CTA = one (batch, head) x 256 query rows; tcgen05.mma.cta_group::1, M = 128.
+//   PAIR = true   a 2-CTA cluster = one (batch, head) x 512 query rows; each CTA keeps its own two 128-row query
+//                 tiles, softmax state and O accumulators, but the K/V block is split between the two CTAs (CTA r stages
+//                 kv rows [64r, 64r+64) of K and head-dim columns [64r, 64r+64) of V) and the leader CTA's MMA thread
+//                 issues every MMA for both (cta_group::2, M = 256).  Why: measured on B200
+//                 (scripts/ubench/mma_rate.cu) a cta_group::1 MMA with M=128 never issues faster than one per ~92 clk
+//                 for N <= 192, i.e. the N=128 MMAs of attention run at 70 % of the tensor peak, while the same MMA
+//                 issued for a CTA pair takes the 64-clk floor, with half the operand traffic per SM.
+//                 "Data is ready" barriers live in the leader CTA (remote arrivals, 2-SM TMA), "data has been
+//                 consumed" barriers are signalled in both CTAs by multicast commits.
+// Other knobs (selected at run time through the "attn_variant" flag; see launch_attention):
+//   POLY_MOD  see softmax_exp_store.
+//   NHAND     number of instalments in which P is handed to the MMA thread (1, 2 or 4).
+//   PP        ping-pong the two query tiles on the MUFU through a pair of named barriers.
+// Warp roles: warps 0..3 softmax of tile 0, 4..7 softmax of tile 1, 8 TMA producer, 9 MMA issuer, 10..11 idle.  The
+// control warps come last on purpose: the sub-partition arbiter favours the highest warp id, and the MMA thread's
+// issue latency sits on the critical path of both tiles.
+template <bool PAIR>
+struct AttnCfg {
+  static constexpr int ST = PAIR ? 4 : 2;                           // K / V ring depth
+  static constexpr int KV_BYTES = PAIR ? TILE_BYTES / 2 : TILE_BYTES;  // per stage: K [64|128 kv x 128 d], V [128 kv x 64|128 d]
+  static constexpr int K_HALF = KV_BYTES / 2;                       // the two 64-wide d halves of a K stage
+  static constexpr int BAR_OFF = 2 * TILE_BYTES + 2 * ST * KV_BYTES;
+  static constexpr size_t SMEM = BAR_OFF + 512;
+};
+
+template <bool PAIR, int POLY_MOD, int NHAND, bool PP, bool LAZY, bool TRACE>
 __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tcgen05_kernel(const __grid_constant__ AttnParams P) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                    // 2 tiles
-  uint8_t* sK = smem + 2 * TILE_BYTES;   // 2 stages
-  uint8_t* sV = smem + 4 * TILE_BYTES;   // 2 stages
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * TILE_BYTES);
-  uint64_t* q_full = bars;           // [1]
-  uint64_t* k_full = bars + 1;       // [2]
-  uint64_t* k_empty = bars + 3;      // [2]
-  uint64_t* v_full = bars + 5;       // [2]
-  uint64_t* v_empty = bars + 7;      // [2]
-  uint64_t* s_full = bars + 9;       // [2] per q tile
-  uint64_t* p_ready = bars + 11;     // [2]
-  uint64_t* o_done = bars + 13;      // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  static_assert(!LAZY || NHAND == 1, "the lazy-max overflow guard needs P to be handed over in one piece");
+  using Cfg = AttnCfg<PAIR>;
+  constexpr int ST = Cfg::ST;
+  constexpr int KVB = Cfg::KV_BYTES;
+  // 128B-swizzled tiles need 1024-byte alignment.  The kernel has no static shared memory, so the dynamic window
+  // starts at the CTA's shared base; declaring the alignment keeps every address a link-time constant, which lets
+  // ptxas hold all MMA operands in uniform registers (checked at run time below).
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sQ = smem;                     // 2 tiles x 32 KB
+  uint8_t* sK = smem + 2 * TILE_BYTES;    // ST stages
+  uint8_t* sV = sK + ST * KVB;            // ST stages
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
+  uint64_t* q_full = bars;                // [1]   (PAIR: leader's is used)
+  uint64_t* k_full = bars + 1;            // [ST]  (leader)
+  uint64_t* v_full = k_full + ST;         // [ST]  (leader)
+  uint64_t* k_empty = v_full + ST;        // [ST]  both CTAs (multicast commit)
+  uint64_t* v_empty = k_empty + ST;       // [ST]
+  uint64_t* s_full = v_empty + ST;        // [2]   per q tile
+  uint64_t* o_done = s_full + 2;          // [2]
+  uint64_t* p_ready = o_done + 2;         // [4 instalments][2 tiles] (leader): one arrival per softmax warp
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_ready + 8);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int bh = blockIdx.x / P.q_pairs;
-  const int qp = blockIdx.x - bh * P.q_pairs;
-  const int q_row0 = qp * 2 * TQ;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0;
+  const int unit = PAIR ? (blockIdx.x >> 1) : blockIdx.x;
+  const int bh = unit / P.q_pairs;  // q_pairs = query groups per (batch, head): 256 rows each (PAIR: 512)
+  const int qp = unit - bh * P.q_pairs;
+  const int q_row0 = PAIR ? (qp * 4 * TQ + static_cast<int>(rank) * 2 * TQ) : qp * 2 * TQ;
+  long long* const trace = (TRACE && P.trace != nullptr && blockIdx.x == 0) ? P.trace : nullptr;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 8 && lane == 0) {
+    if ((smem_u32(smem) & 1023u) != 0) {
+      printf("fluxb200: attention shared memory base is not 1024-byte aligned\n");
+      __trap();
+    }
     tma_prefetch_desc(&P.tmap_q);
     tma_prefetch_desc(&P.tmap_k);
     tma_prefetch_desc(&P.tmap_v);
     mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < ST; ++i) {
       mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], 1);
       mbar_init(&v_full[i], 1);
+      mbar_init(&k_empty[i], 1);
       mbar_init(&v_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_ready[i], 128);
       mbar_init(&o_done[i], 1);
     }
+    for (int i = 0; i < 8; ++i) mbar_init(&p_ready[i], PAIR ? 8 : 4);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (warp == 9) {
+    if (PAIR) tmem_alloc_2sm(tmem_slot, 512); else tmem_alloc(tmem_slot, 512);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();  // (peer) barriers initialised before any arrival
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  // The CTA owns all 512 TMEM columns, so the allocation starts at column 0 / lane 0; the kernel relies on it so
+  // that TMEM addresses are compile-time constants.
+  if (*tmem_slot != 0) {
+    if (threadIdx.x == 0) printf("fluxb200: unexpected TMEM base %u\n", *tmem_slot);
+    __trap();
+  }
+  constexpr uint32_t TM_S = 0, TM_O = 256;
+  // everything above overlapped the previous kernel's tail; q/k/v are valid from here on
+  pdl_launch_dependents();
+  pdl_wait();
 
-  if (warp == 0) {
-    if (lane == 0) {
-      // ---------------- TMA producer ----------------
-      mbar_arrive_expect_tx(q_full, 2 * TILE_BYTES);
-      for (int g = 0; g < 2; ++g) {
-        tma_load_3d(sQ + g * TILE_BYTES, &P.tmap_q, q_full, 0, q_row0 + g * TQ, bh);
-        tma_load_3d(sQ + g * TILE_BYTES + HALF_BYTES, &P.tmap_q, q_full, 64, q_row0 + g * TQ, bh);
-      }
-      for (int j = 0; j < P.nkv; ++j) {
-        const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        mbar_wait(&k_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&k_full[st], TILE_BYTES);
-        tma_load_3d(sK + st * TILE_BYTES, &P.tmap_k, &k_full[st], 0, j * TKV, bh);
-        tma_load_3d(sK + st * TILE_BYTES + HALF_BYTES, &P.tmap_k, &k_full[st], 64, j * TKV, bh);
-        mbar_wait(&v_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&v_full[st], TILE_BYTES);
-        tma_load_3d(sV + st * TILE_BYTES, &P.tmap_v, &v_full[st], 0, j * TKV, bh);
-        tma_load_3d(sV + st * TILE_BYTES + HALF_BYTES, &P.tmap_v, &v_full[st], 64, j * TKV, bh);
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      // ---------------- MMA issuer ----------------
-      constexpr uint32_t idesc_s = umma_idesc_bf16(TQ, TKV, 0, 0);  // Q (K-major) x K (K-major)
-      constexpr uint32_t idesc_o = umma_idesc_bf16(TQ, HD, 0, 1);   // P (TMEM)    x V (MN-major)
-      // The issuing thread is a single lane: keep its instruction stream short.  All shared-memory descriptors are
-      // built once; inside the loops a descriptor is `base + compile-time constant` (the address field is the low
-      // 14 bits in 16-byte units and smem < 256 KB, so the add never carries into the next field).
-      const uint64_t qd0 = umma_smem_desc_sw128(smem_u32(sQ), 16, 1024);
-      const uint64_t qd1 = umma_smem_desc_sw128(smem_u32(sQ) + TILE_BYTES, 16, 1024);
-      const uint64_t kd0 = umma_smem_desc_sw128(smem_u32(sK), 16, 1024);
-      const uint64_t kd1 = umma_smem_desc_sw128(smem_u32(sK) + TILE_BYTES, 16, 1024);
-      const uint64_t vd0 = umma_smem_desc_sw128(smem_u32(sV), HALF_BYTES, 1024);
-      const uint64_t vd1 = umma_smem_desc_sw128(smem_u32(sV) + TILE_BYTES, HALF_BYTES, 1024);
-      auto issue_s = [&](int g, int st) {
-        const uint64_t qd = g ? qd1 : qd0;
-        const uint64_t kd = st ? kd1 : kd0;
-        const uint32_t ts = tmem_base + g * 128;
-#pragma unroll
-        for (int k = 0; k < HD / 16; ++k) {
-          // d 0..63 sit in the first swizzle-atom column, 64..127 in the second; 32 B per k-step inside an atom
-          const uint64_t off = static_cast<uint64_t>(((k >> 2) * HALF_BYTES + (k & 3) * 32) >> 4);
-          umma_ss(ts, qd + off, kd + off, idesc_s, k != 0);
-        }
-      };
-      auto issue_pv = [&](int g, int st, bool accumulate) {
-        const uint64_t vd = st ? vd1 : vd0;
-        const uint32_t to = tmem_base + 256 + g * 128;
-        const uint32_t tp = tmem_base + g * 128;
-#pragma unroll
-        for (int k = 0; k < TKV / 16; ++k) {
-          // A: 16 bf16 of P per row = 8 TMEM columns per k-step. B: 16 kv rows = 2048 B per k-step;
-          // the two 64-wide d chunks are HALF_BYTES apart (LBO), 8-row groups 1024 B apart (SBO).
-          umma_ts(to, tp + k * 8, vd + static_cast<uint64_t>((k * 2048) >> 4), idesc_o, accumulate || (k != 0));
-        }
-      };
-      mbar_wait(q_full, 0);
-      mbar_wait(&k_full[0], 0);
-      tc_fence_after();
-      issue_s(0, 0);
-      tc_commit(&s_full[0]);
-      issue_s(1, 0);
-      tc_commit(&s_full[1]);
-      tc_commit(&k_empty[0]);  // K_0 consumed by S0_0 / S1_0
-      for (int j = 0; j < P.nkv; ++j) {
-        const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        const bool has_next = (j + 1 < P.nkv);
-        const int nst = (j + 1) & 1;
-        mbar_wait(&v_full[st], ph);
-        if (has_next) mbar_wait(&k_full[nst], ((j + 1) >> 1) & 1);
-        for (int g = 0; g < 2; ++g) {
-          mbar_wait(&p_ready[g], j & 1);
-          tc_fence_after();
-          issue_pv(g, st, j > 0);
-          if (has_next) {
-            issue_s(g, nst);
-            tc_commit(&s_full[g]);
-          } else {
-            tc_commit(&o_done[g]);
+  // Register file: 3 warps per SM sub-partition cap every thread at 168 registers at launch; the control warpgroup
+  // hands part of its share to the softmax warpgroups, which keep a whole 128-column score row in registers
+  // (120 + 2 x 192 = 3 x 168).
+  if (warp >= 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 120;");
+    if (warp == 8) {
+      if (lane == 0) {
+        // ---------------- TMA producer (PAIR: one per CTA; bytes are credited to the leader's barriers) ----------------
+        if (PAIR) {
+          const uint32_t qbar = mapa_u32(smem_u32(q_full), 0);
+          if (rank == 0) mbar_arrive_expect_tx(q_full, 2 * 2 * TILE_BYTES);
+          for (int g = 0; g < 2; ++g) {
+            tma_load_3d_2sm(sQ + g * TILE_BYTES, &P.tmap_q, qbar, 0, q_row0 + g * TQ, bh);
+            tma_load_3d_2sm(sQ + g * TILE_BYTES + HALF_BYTES, &P.tmap_q, qbar, 64, q_row0 + g * TQ, bh);
+          }
+        } else {
+          mbar_arrive_expect_tx(q_full, 2 * TILE_BYTES);
+          for (int g = 0; g < 2; ++g) {
+            tma_load_3d(sQ + g * TILE_BYTES, &P.tmap_q, q_full, 0, q_row0 + g * TQ, bh);
+            tma_load_3d(sQ + g * TILE_BYTES + HALF_BYTES, &P.tmap_q, q_full, 64, q_row0 + g * TQ, bh);
           }
         }
-        tc_commit(&v_empty[st]);
-        if (has_next) tc_commit(&k_empty[nst]);  // K_{j+1} fully consumed by S0/S1_{j+1}
+        int st = 0;
+        uint32_t ph = 0;
+        for (int j = 0; j < P.nkv; ++j) {
+          uint8_t* dk = sK + st * KVB;
+          uint8_t* dv = sV + st * KVB;
+          mbar_wait(&k_empty[st], ph ^ 1);
+          if (PAIR) {
+            const uint32_t kbar = mapa_u32(smem_u32(&k_full[st]), 0);
+            if (rank == 0) mbar_arrive_expect_tx(&k_full[st], 2 * KVB);
+            tma_load_3d_2sm(dk, &P.tmap_k, kbar, 0, j * TKV + static_cast<int>(rank) * 64, bh);
+            tma_load_3d_2sm(dk + Cfg::K_HALF, &P.tmap_k, kbar, 64, j * TKV + static_cast<int>(rank) * 64, bh);
+          } else {
+            mbar_arrive_expect_tx(&k_full[st], KVB);
+            tma_load_3d(dk, &P.tmap_k, &k_full[st], 0, j * TKV, bh);
+            tma_load_3d(dk + Cfg::K_HALF, &P.tmap_k, &k_full[st], 64, j * TKV, bh);
+          }
+          mbar_wait(&v_empty[st], ph ^ 1);
+          if (PAIR) {
+            const uint32_t vbar = mapa_u32(smem_u32(&v_full[st]), 0);
+            if (rank == 0) mbar_arrive_expect_tx(&v_full[st], 2 * KVB);
+            tma_load_3d_2sm(dv, &P.tmap_v, vbar, static_cast<int>(rank) * 64, j * TKV, bh);
+          } else {
+            mbar_arrive_expect_tx(&v_full[st], KVB);
+            tma_load_3d(dv, &P.tmap_v, &v_full[st], 0, j * TKV, bh);
+            tma_load_3d(dv + HALF_BYTES, &P.tmap_v, &v_full[st], 64, j * TKV, bh);
+          }
+          if (++st == ST) st = 0, ph ^= 1;
+        }
+      }
+    } else if (warp == 9) {
+      if (rank == 0) {
+        // ---------------- MMA issuer (PAIR: leader CTA only) ----------------
+        // The whole warp walks the loop (uniform control flow); one elected lane issues the MMAs and commits.
+        const bool el = elect_one() != 0;
+        // Everything this thread feeds to tcgen05.mma is a compile-time constant (shared-memory symbol + offset, TMEM
+        // column, stage index through full unrolling): the operands stay in uniform registers and an MMA costs a
+        // handful of issue slots.
+        constexpr uint32_t idesc_s = umma_idesc_bf16(PAIR ? 2 * TQ : TQ, TKV, 0, 0);  // Q (K-major) x K (K-major)
+        constexpr uint32_t idesc_o = umma_idesc_bf16(PAIR ? 2 * TQ : TQ, HD, 0, 1);   // P (TMEM) x V (MN-major)
+        const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV);
+        auto wait_full = [&](uint64_t* bar, uint32_t parity) {
+          if (PAIR) mbar_wait_cluster(bar, parity); else mbar_wait(bar, parity);
+        };
+        auto commit = [&](uint64_t* bar) {
+          if (el) {
+            if (PAIR) tc_commit_2sm(bar, 3); else tc_commit(bar);
+          }
+        };
+        auto issue_s = [&](int g, int st) {
+          const uint64_t qd = umma_smem_desc_sw128(aQ + g * TILE_BYTES, 16, 1024);
+          const uint64_t kd = umma_smem_desc_sw128(aK + st * KVB, 16, 1024);
+          if (el)
+#pragma unroll
+          for (int k = 0; k < HD / 16; ++k) {
+            // d 0..63 sit in the first swizzle-atom column, 64..127 in the second; 32 B per k-step inside an atom
+            const uint64_t offq = static_cast<uint64_t>(((k >> 2) * HALF_BYTES + (k & 3) * 32) >> 4);
+            const uint64_t offk = static_cast<uint64_t>(((k >> 2) * Cfg::K_HALF + (k & 3) * 32) >> 4);
+            if (PAIR) umma_ss_2sm(TM_S + g * 128, qd + offq, kd + offk, idesc_s, k != 0);
+            else      umma_ss(TM_S + g * 128, qd + offq, kd + offk, idesc_s, k != 0);
+          }
+        };
+        // kv rows [k0*16, k1*16) of O_g += P_g.V
+        auto issue_pv = [&](int g, int st, bool accumulate, int k0, int k1) {
+          // B: 16 kv rows = 2048 B per k-step; 64-wide d chunks HALF_BYTES apart (LBO; PAIR: one chunk per CTA),
+          // 8-row groups 1024 B apart (SBO).  A: 16 bf16 of P per row = 8 TMEM columns per k-step.
+          const uint64_t vd = umma_smem_desc_sw128(aV + st * KVB, HALF_BYTES, 1024);
+          if (el)
+#pragma unroll
+          for (int k = k0; k < k1; ++k) {
+            const uint64_t off = static_cast<uint64_t>((k * 2048) >> 4);
+            if (PAIR) umma_ts_2sm(TM_O + g * 128, TM_S + g * 128 + k * 8, vd + off, idesc_o, accumulate || (k != 0));
+            else      umma_ts(TM_O + g * 128, TM_S + g * 128 + k * 8, vd + off, idesc_o, accumulate || (k != 0));
+          }
+        };
+        wait_full(q_full, 0);
+        wait_full(&k_full[0], 0);
+        tc_fence_after();
+        issue_s(0, 0);
+        commit(&s_full[0]);
+        issue_s(1, 0);
+        commit(&s_full[1]);
+        commit(&k_empty[0]);  // K_0 consumed by S0_0 / S1_0
+        int st = 0;
+        uint32_t ph = 0;
+#pragma unroll 1
+        for (int j = 0; j < P.nkv; ++j) {
+          {
+            const bool has_next = (j + 1 < P.nkv);
+            const int nst = (st + 1 == ST) ? 0 : st + 1;
+            const uint32_t nph = (st + 1 == ST) ? (ph ^ 1) : ph;
+            wait_full(&v_full[st], ph);
+            if (has_next) wait_full(&k_full[nst], nph);
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+#pragma unroll
+              for (int hnd = 0; hnd < NHAND; ++hnd) {
+                wait_full(&p_ready[hnd * 2 + g], j & 1);
+                tc_fence_after();
+                if (TRACE && hnd == 0 && el && trace && j < 64) trace[(j * 2 + g) * 8 + 6] = clock64();
+                issue_pv(g, st, j > 0, hnd * (8 / NHAND), (hnd + 1) * (8 / NHAND));
+              }
+              if (has_next) {
+                issue_s(g, nst);
+                commit(&s_full[g]);
+              } else {
+                commit(&o_done[g]);
+              }
+              if (TRACE && el && trace && j < 64) trace[(j * 2 + g) * 8 + 7] = clock64();
+            }
+            commit(&v_empty[st]);
+            if (has_next) commit(&k_empty[nst]);  // K_{j+1} fully consumed by S0/S1_{j+1}
+            st = nst, ph = nph;
+          }
+        }
       }
     }
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
     // ---------------- softmax / correction / epilogue ----------------
-    const int g = (warp - 2) >> 2;  // query tile
-    const int q = warp & 3;         // TMEM lane quarter
-    const int r = q * 32 + lane;    // row in tile
+    const int g = warp >> 2;      // query tile
+    const int q = warp & 3;       // TMEM lane quarter
+    const int r = q * 32 + lane;  // row in tile
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
-    const uint32_t tS = tmem_base + g * 128 + lane_off;
-    const uint32_t tO = tmem_base + 256 + g * 128 + lane_off;
+    const uint32_t tS = TM_S + g * 128 + lane_off;
+    const uint32_t tO = TM_O + g * 128 + lane_off;
     const float sl2 = P.sl2;
     float m_run = -INFINITY;  // running (possibly stale) row max of raw scores
     float l_run = 0.f;
+    float m_pend = -INFINITY;  // LAZY: max over all blocks processed so far (>= m_run)
+    long long* const tr = (TRACE && trace && r == 0) ? trace : nullptr;
+    const uint32_t pbar0 = PAIR ? mapa_u32(smem_u32(&p_ready[g]), 0) : smem_u32(&p_ready[g]);  // + 16 B per instalment
+    auto arrive_p = [&](int hnd) {
+      if (PAIR) mbar_arrive_cluster_relaxed(pbar0 + hnd * 16);
+      else      mbar_arrive(&p_ready[hnd * 2 + g]);
+    };
     // The two tiles' softmax warps share the SM's MUFU unit.  A ping-pong pair of named barriers lets only one tile
     // be in its exp2 phase at a time, which keeps the tiles in anti-phase: while tile g exponentiates, the tensor
     // core runs the other tile's P.V and next Q.K^T.
-    if (PINGPONG && g == 1) named_bar_arrive(1, 256);  // tile 0 goes first
+    if (PP && g == 1) named_bar_arrive(1, 256);  // tile 0 goes first
 
     for (int j = 0; j < P.nkv; ++j) {
       mbar_wait(&s_full[g], j & 1);
       tc_fence_after();
+      if (TRACE && tr && j < 64) tr[(j * 2 + g) * 8 + 0] = clock64();
       uint32_t s[128];
       tmem_ld32(tS + 0, &s[0]);
       tmem_ld32(tS + 32, &s[32]);
       tmem_ld32(tS + 64, &s[64]);
       tmem_ld32(tS + 96, &s[96]);
       tc_wait_ld();
+      if (TRACE && tr && j < 64) tr[(j * 2 + g) * 8 + 1] = clock64();
       const int kv_valid = P.L - j * TKV;  // >= 128 except on the last block
-      float bmax = -INFINITY;
-      if (kv_valid >= TKV) {
+      if (kv_valid < TKV) {
 #pragma unroll
-        for (int i = 0; i < 128; ++i) bmax = fmaxf(bmax, __uint_as_float(s[i]));
-      } else {
-#pragma unroll
-        for (int i = 0; i < 128; ++i) {
+        for (int i = 0; i < 128; ++i)
           if (i >= kv_valid) s[i] = __float_as_uint(-INFINITY);
-          bmax = fmaxf(bmax, __uint_as_float(s[i]));
-        }
       }
-      const float m_new = fmaxf(m_run, bmax);
+      // Candidate for the running max.  Eager: this block's row max (four independent 3-input max chains).  LAZY: for
+      // j > 0 the max of everything up to the PREVIOUS block (m_pend, collected under that block's exponentials), so
+      // nothing stands between the TMEM load and the exp2 phase.  P may then exceed 1 (bounded by the guard below);
+      // bf16/fp32 are scale-invariant, so precision is unchanged.
+      float m_new;
+      if (!LAZY || j == 0) {
+        float bm0 = -INFINITY, bm1 = -INFINITY, bm2 = -INFINITY, bm3 = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 128; i += 8) {
+          bm0 = fmax3(bm0, __uint_as_float(s[i + 0]), __uint_as_float(s[i + 1]));
+          bm1 = fmax3(bm1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
+          bm2 = fmax3(bm2, __uint_as_float(s[i + 4]), __uint_as_float(s[i + 5]));
+          bm3 = fmax3(bm3, __uint_as_float(s[i + 6]), __uint_as_float(s[i + 7]));
+        }
+        m_new = fmaxf(m_run, fmaxf(fmaxf(bm0, bm1), fmaxf(bm2, bm3)));
+      } else {
+        m_new = m_pend;
+      }
       // lazy rescale: keep a stale max while exp2 stays below 2^8
       const bool need = (m_new - m_run) * sl2 > 8.0f;
       if (__any_sync(0xffffffffu, need)) {
@@ -227,26 +447,44 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tcgen05_kernel(const
           }
         }
       }
-      const float mb = m_run * sl2;
-      float lsum = 0.f;
-      if (PINGPONG) named_bar_sync(1 + g, 256);  // wait for this tile's turn on the MUFU
+      const float nmb = -m_run * sl2;
+      if (TRACE && tr && j < 64) tr[(j * 2 + g) * 8 + 2] = clock64();
+      if (PP) named_bar_sync(1 + g, 256);  // wait for this tile's turn on the MUFU
+      if (TRACE && tr && j < 64) tr[(j * 2 + g) * 8 + 3] = clock64();
+      const float l_before = l_run;
+      float bmax_blk = -INFINITY;
+      softmax_exp_store<POLY_MOD, NHAND, LAZY>(s, tS, sl2, nmb, l_run, bmax_blk, lane, arrive_p);
+      if (LAZY) {
+        m_pend = fmaxf(m_run, bmax_blk);
+        // Overflow guard (never taken on sane data): a score of this block exceeds everything seen before by more
+        // than 2^64.  Nothing of P has been handed over yet, so rescale O and l to the new max and redo the block.
+        const bool ovf = (m_pend - m_run) * sl2 > 64.0f;
+        if (__any_sync(0xffffffffu, ovf)) {
+          const float factor = ex2_approx((m_run - m_pend) * sl2);
+          m_run = m_pend;
+          l_run = l_before * factor;
+          tc_wait_st();
+          if (j > 0) {
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+              uint32_t o[32];
+              tmem_ld32(tO + c * 32, o);
+              tc_wait_ld();
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float p0 = ex2_approx(fmaf(__uint_as_float(s[c * 32 + 2 * i]), sl2, -mb));
-          float p1 = ex2_approx(fmaf(__uint_as_float(s[c * 32 + 2 * i + 1]), sl2, -mb));
-          lsum += p0 + p1;
-          pk[i] = pack_bf16(p0, p1);
+              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
+              tmem_st32(tO + c * 32, o);
+            }
+          }
+          softmax_exp_store<POLY_MOD, NHAND, false>(s, tS, sl2, -m_run * sl2, l_run, bmax_blk, lane, arrive_p);
         }
-        tmem_st16(tS + c * 16, pk);
       }
-      l_run += lsum;
-      if (PINGPONG) named_bar_arrive(2 - g, 256);  // hand the MUFU to the other tile
+      if (TRACE && tr && j < 64) tr[(j * 2 + g) * 8 + 4] = clock64();
+      if (PP) named_bar_arrive(2 - g, 256);  // hand the MUFU to the other tile
       tc_wait_st();
       tc_fence_before();
-      mbar_arrive(&p_ready[g]);
+      __syncwarp();
+      if (lane == 0) arrive_p(NHAND - 1);
+      if (TRACE && tr && j < 64) tr[(j * 2 + g) * 8 + 5] = clock64();
     }
 
     // epilogue: O / l -> bf16 -> global
@@ -283,12 +521,33 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tcgen05_kernel(const
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
+  // PAIR: the peer's shared memory and barriers stay alive until every MMA / multicast commit has landed
+  if (PAIR) cluster_sync_all(); else __syncthreads();
+  if (warp == 9) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (PAIR) tmem_dealloc_2sm(0, 512); else tmem_dealloc(0, 512);
   }
 }
+
+typedef void (*AttnKernel)(const AttnParams);
+struct AttnVariant {
+  AttnKernel fn, fn_traced;
+  int mode;  // 0: one CTA per 256 query rows; 1: 2-CTA clusters, 512 query rows per pair
+  const char* what;
+};
+#define FB_ATTN_VARIANT(PAIR, POLY, NHAND, PP, LAZY, WHAT)                                             \
+  {attention_tcgen05_kernel<PAIR, POLY, NHAND, PP, LAZY, false>,                                       \
+   attention_tcgen05_kernel<PAIR, POLY, NHAND, PP, LAZY, true>, PAIR ? 1 : 0, WHAT}
+// run-time selectable builds of the kernel ("attn_variant" flag); index 0 is the production default
+static const AttnVariant kAttnVariants[] = {
+    FB_ATTN_VARIANT(false, 4, 1, true, false, "1 CTA, every 4th exp2 pair on the FMA pipe, whole-P handoff (production)"),
+    FB_ATTN_VARIANT(false, 0, 1, true, false, "1 CTA, all exp2 on the MUFU"),
+    FB_ATTN_VARIANT(false, 4, 4, true, false, "1 CTA, poly 1/4, P in 4 instalments"),
+    FB_ATTN_VARIANT(false, 4, 1, true, true, "1 CTA, poly 1/4, lazy max"),
+    FB_ATTN_VARIANT(true, 4, 1, true, false, "CTA pair, poly 1/4"),
+    FB_ATTN_VARIANT(true, 4, 4, true, false, "CTA pair, poly 1/4, P in 4 instalments"),
+};
+static constexpr int kNumAttnVariants = sizeof(kAttnVariants) / sizeof(kAttnVariants[0]);
 
 int launch_attention(const AttnDesc& d, cudaStream_t stream) {
   FB_REQUIRE(d.q && d.k && d.v, "attention: null q/k/v");
@@ -298,10 +557,17 @@ int launch_attention(const AttnDesc& d, cudaStream_t stream) {
   FB_REQUIRE(d.l_split == d.L || d.out_b != nullptr, "attention: out_b required");
   static bool attr_set = false;
   if (!attr_set) {
-    FB_CHECK_CUDA(cudaFuncSetAttribute(attention_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(ATT_SMEM)));
+    for (int i = 0; i < kNumAttnVariants; ++i) {
+      const int bytes = static_cast<int>(kAttnVariants[i].mode == 1 ? AttnCfg<true>::SMEM : AttnCfg<false>::SMEM);
+      FB_CHECK_CUDA(cudaFuncSetAttribute(kAttnVariants[i].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      FB_CHECK_CUDA(cudaFuncSetAttribute(kAttnVariants[i].fn_traced, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    }
     attr_set = true;
   }
+  const int variant = get_flag("attn_variant");
+  FB_REQUIRE(variant >= 0 && variant < kNumAttnVariants, "attention: unknown attn_variant");
+  const int mode = kAttnVariants[variant].mode;
+  const bool pair = mode == 1;
   AttnParams P;
   memset(&P, 0, sizeof(P));
   const uint64_t bh = static_cast<uint64_t>(d.B) * d.H;
@@ -309,18 +575,23 @@ int launch_attention(const AttnDesc& d, cudaStream_t stream) {
   CUtensorMap* maps[3] = {&P.tmap_q, &P.tmap_k, &P.tmap_v};
   for (int i = 0; i < 3; ++i) {
     FB_REQUIRE((reinterpret_cast<uintptr_t>(ptrs[i]) & 15) == 0, "attention: q/k/v must be 16-byte aligned");
-    int rc = encode_tmap_3d(maps[i], ptrs[i], HD, d.L, bh, HD * 2, static_cast<uint64_t>(d.L) * HD * 2, 64, TQ, 1);
+    // pair mode: each CTA stages 64 of the 128 kv rows of a K block (V: all 128 kv rows x 64 of the 128 columns)
+    const uint32_t box_rows = (pair && i == 1) ? TKV / 2 : TQ;
+    int rc = encode_tmap_3d(maps[i], ptrs[i], HD, d.L, bh, HD * 2, static_cast<uint64_t>(d.L) * HD * 2, 64, box_rows, 1);
     if (rc) return rc;
   }
   P.B = d.B, P.H = d.H, P.L = d.L, P.l_split = d.l_split;
-  P.q_pairs = (d.L + 2 * TQ - 1) / (2 * TQ);
+  P.q_pairs = pair ? (d.L + 4 * TQ - 1) / (4 * TQ) : (d.L + 2 * TQ - 1) / (2 * TQ);
   P.nkv = (d.L + TKV - 1) / TKV;
   P.sl2 = d.scale * 1.4426950408889634f;
   P.out_a = d.out_a, P.out_b = d.out_b, P.ld_a = d.ld_a, P.ld_b = d.ld_b;
-  const int grid = static_cast<int>(bh) * P.q_pairs;
+  P.trace = d.trace;
+  const int grid = static_cast<int>(bh) * P.q_pairs * (pair ? 2 : 1);
   ProfScope _ps(KK_ATTN, 4.0 * bh * static_cast<double>(d.L) * d.L * HD, 4.0 * bh * d.L * HD * 2.0, stream);
   count_launch(KK_ATTN);
-  attention_tcgen05_kernel<<<grid, ATT_THREADS, ATT_SMEM, stream>>>(P);
+  const AttnKernel kern = d.trace ? kAttnVariants[variant].fn_traced : kAttnVariants[variant].fn;
+  FB_CHECK_CUDA(launch_ex(kern, dim3(grid), dim3(ATT_THREADS), pair ? AttnCfg<true>::SMEM : AttnCfg<false>::SMEM, stream,
+                          pair ? 2 : 1, get_flag("pdl") != 0, P));
   FB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -59,6 +59,16 @@ int fluxb200_sdpa(const void* q, const void* k, const void* v, void* out, int32_
   return launch_attention(d, static_cast<cudaStream_t>(stream));
 }
 
+int fluxb200_debug_sdpa_trace(const void* q, const void* k, const void* v, void* out, int32_t B, int32_t H, int32_t L,
+                              float scale, void* trace, fluxb200_stream_t stream) {
+  AttnDesc d;
+  d.q = static_cast<const bf16*>(q), d.k = static_cast<const bf16*>(k), d.v = static_cast<const bf16*>(v);
+  d.B = B, d.H = H, d.L = L, d.scale = scale;
+  d.out_b = static_cast<bf16*>(out), d.ld_b = static_cast<int64_t>(H) * 128, d.l_split = 0;
+  d.trace = static_cast<long long*>(trace);
+  return launch_attention(d, static_cast<cudaStream_t>(stream));
+}
+
 int fluxb200_layernorm_modulate(const void* x, const void* shift, const void* scale, int64_t mod_bstride, void* out,
                                 int32_t batch, int32_t rows_per_batch, int32_t dim, float eps,
                                 fluxb200_stream_t stream) {

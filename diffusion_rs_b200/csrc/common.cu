@@ -57,10 +57,24 @@ ProfScope::~ProfScope() {
   cudaEventRecord(g_prof_recs[slot].b, stream);
 }
 
-static int g_flag_qkrope = 1, g_flag_pair = -1, g_flag_fdq = 0;
+static int g_flag_qkrope = 1, g_flag_pair = -1, g_flag_fdq = 0, g_flag_attn = -1, g_flag_pdl = -1;
 int get_flag(const char* name) {
   if (!strcmp(name, "qkrope_fusion")) return g_flag_qkrope;
   if (!strcmp(name, "fused_dequant")) return g_flag_fdq;
+  if (!strcmp(name, "pdl")) {
+    if (g_flag_pdl < 0) {
+      const char* e = getenv("FLUXB200_PDL");
+      g_flag_pdl = (e && e[0] == '0') ? 0 : 1;
+    }
+    return g_flag_pdl;
+  }
+  if (!strcmp(name, "attn_variant")) {
+    if (g_flag_attn < 0) {
+      const char* e = getenv("FLUXB200_ATTN_VARIANT");
+      g_flag_attn = e ? atoi(e) : 0;
+    }
+    return g_flag_attn;
+  }
   if (!strcmp(name, "gemm_pair")) {
     if (g_flag_pair < 0) {
       const char* e = getenv("FLUXB200_GEMM_SINGLE_CTA");
@@ -178,6 +192,8 @@ int fluxb200_set_flag(const char* name, int value) {
   if (!strcmp(name, "qkrope_fusion")) { fb::g_flag_qkrope = value ? 1 : 0; return 0; }
   if (!strcmp(name, "gemm_pair")) { fb::g_flag_pair = value ? 1 : 0; return 0; }
   if (!strcmp(name, "fused_dequant")) { fb::g_flag_fdq = value ? 1 : 0; return 0; }
+  if (!strcmp(name, "attn_variant")) { fb::g_flag_attn = value; return 0; }
+  if (!strcmp(name, "pdl")) { fb::g_flag_pdl = value ? 1 : 0; return 0; }
   return fb::fail(std::string("set_flag: unknown flag ") + name);
 }
 void fluxb200_profile_enable(int on) {

@@ -37,6 +37,8 @@ __global__ void __launch_bounds__(128, 4) ln_modulate_kernel(const bf16* __restr
   constexpr int VEC = D / 256;  // uint4 (8 bf16) per lane
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 4 + warp;
+  pdl_launch_dependents();
+  pdl_wait();  // x is the previous kernel's output
   if (row >= total_rows) return;
   const int b = row / rows_per_batch;
   const int i = row - b * rows_per_batch;
@@ -87,8 +89,8 @@ int launch_ln_modulate(const bf16* x, long long in_bstride_rows, int in_row_off,
   const int total = rows_per_batch * batch;
   ProfScope _ps(KK_LN_MOD, 0, 4.0 * total * D, stream);
   count_launch(KK_LN_MOD, 1);
-  ln_modulate_kernel<3072><<<(total + 3) / 4, 128, 0, stream>>>(x, in_bstride_rows, in_row_off, rows_per_batch, total,
-                                                                shift, scale, mod_bstride, out, eps);
+  FB_CHECK_CUDA(launch_ex(ln_modulate_kernel<3072>, dim3((total + 3) / 4), dim3(128), 0, stream, 1, get_flag("pdl") != 0,
+                          x, in_bstride_rows, in_row_off, rows_per_batch, total, shift, scale, mod_bstride, out, eps));
   FB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

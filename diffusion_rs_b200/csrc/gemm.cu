@@ -505,6 +505,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   if (CTA2) cluster_sync_all(); else __syncthreads();  // peer barriers must be initialised before remote arrivals
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
+  // everything above overlapped the previous kernel's tail; its outputs (our A operand, residual, ...) are valid from here
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -892,21 +895,18 @@ int launch_gemm(const GemmDesc* descs, int count, cudaStream_t stream) {
   }
   ProfScope _ps(KK_GEMM, flops, bytes, stream);
   count_launch(KK_GEMM);
+  const bool pdl = get_flag("pdl") != 0;
   if (use_pair) {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(2 * std::min(tile, num_sms() / 2));
-    cfg.blockDim = dim3(GEMM_THREADS);
-    cfg.dynamicSmemBytes = quant_b ? GemmCfg<true, true>::SMEM : GemmCfg<true, false>::SMEM;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr, cfg.numAttrs = 1;
-    if (quant_b) FB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<true, true>, P));
-    else         FB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<true, false>, P));
+    const dim3 grid(2 * std::min(tile, num_sms() / 2));
+    if (quant_b)
+      FB_CHECK_CUDA(launch_ex(gemm_tcgen05_kernel<true, true>, grid, dim3(GEMM_THREADS), GemmCfg<true, true>::SMEM, stream,
+                              2, pdl, P));
+    else
+      FB_CHECK_CUDA(launch_ex(gemm_tcgen05_kernel<true, false>, grid, dim3(GEMM_THREADS), GemmCfg<true, false>::SMEM,
+                              stream, 2, pdl, P));
   } else {
-    const int grid = std::min(tile, num_sms());
-    gemm_tcgen05_kernel<false, false><<<grid, GEMM_THREADS, GemmCfg<false>::SMEM, stream>>>(P);
+    FB_CHECK_CUDA(launch_ex(gemm_tcgen05_kernel<false, false>, dim3(std::min(tile, num_sms())), dim3(GEMM_THREADS),
+                            GemmCfg<false>::SMEM, stream, 1, pdl, P));
   }
   FB_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -6,6 +6,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <utility>
 
 typedef __nv_bfloat16 bf16;
 
@@ -116,6 +117,29 @@ struct QuantB {
   int count = 0;
 };
 
+// Launch helper for the hot kernels: optional 2-CTA cluster + programmatic dependent launch (the "pdl" flag).  Only
+// kernels that execute griddepcontrol.wait before touching global memory may be launched through it.
+template <class... KArgs, class... Args>
+inline cudaError_t launch_ex(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                             int cluster_x, bool pdl, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  unsigned n = 0;
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster_x, attr[n].val.clusterDim.y = 1, attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr, cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
 // runtime switches (A/B testing): "qkrope_fusion" (default 1), "gemm_pair" (default 1)
 int get_flag(const char* name);
 // One persistent launch over up to 4 problems (grouped): img + txt streams share the machine.
@@ -132,6 +156,7 @@ struct AttnDesc {
   bf16* out_b = nullptr;
   int64_t ld_b = 0;
   int l_split = 0;
+  long long* trace = nullptr;  // debug: device buffer of 64*2*8 clock stamps written by CTA 0
 };
 int launch_attention(const AttnDesc& d, cudaStream_t stream);
 

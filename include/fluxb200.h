@@ -60,6 +60,11 @@ int fluxb200_linear_quant(const void* a, int64_t lda, const void* packed, const 
 int fluxb200_sdpa(const void* q, const void* k, const void* v, void* out, int32_t B, int32_t H, int32_t L,
                   float scale, fluxb200_stream_t stream);
 
+/* Debug/profiling twin of fluxb200_sdpa: additionally records clock64 stamps of CTA 0's pipeline stages into `trace`
+ * (device buffer of 64*2*8 int64: [kv block][query tile][stage]); used by scripts/attn_trace.py only. */
+int fluxb200_debug_sdpa_trace(const void* q, const void* k, const void* v, void* out, int32_t B, int32_t H, int32_t L,
+                              float scale, void* trace, fluxb200_stream_t stream);
+
 /* out = modulate(LayerNorm(x)) = (LN(x) * (1 + scale[b])) + shift[b]; x,out bf16 [B*rows, 3072].
  * Replaces nn::LayerNorm::forward + ModulationOut::scale_shift (model.rs:33-38, 217-221). */
 int fluxb200_layernorm_modulate(const void* x, const void* shift, const void* scale, int64_t mod_bstride, void* out,

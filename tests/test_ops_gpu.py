@@ -105,6 +105,28 @@ def test_sdpa(fluxlib, B, H, L):
     assert mx < 0.05, (mx, rel)
 
 
+@pytest.mark.parametrize("boost", [4.0, 60.0])
+def test_sdpa_late_large_scores(fluxlib, boost):
+    """Keys of the later kv blocks are much larger than the early ones, so the running max jumps after the first
+    blocks: x4 exercises the deferred (one block late) rescale of the lazy-max softmax, x60 its overflow guard
+    (scores exceed everything seen before by more than 2^64)."""
+    from diffusion_rs_b200 import ops
+    B, H, L = 1, 2, 1000
+    q = _rand((B, H, L, 128), 23)
+    k = _rand((B, H, L, 128), 24)
+    v = _rand((B, H, L, 128), 25)
+    k[:, :, 300:600] *= boost
+    k[:, :, 900:] *= boost * 1.5
+    scale = 1.0 / math.sqrt(128)
+    y = ops.sdpa(q, k, v, scale)
+    torch.cuda.synchronize()
+    ref = O.sdpa_f32(q.float(), k.float(), v.float(), scale)
+    ref = O.rb(ref).transpose(1, 2).reshape(B, L, H * 128)
+    assert torch.isfinite(y.float()).all()
+    mx, rel = _err(y, ref)
+    assert rel < 1e-2, (mx, rel)
+
+
 def test_layernorm_modulate(fluxlib):
     from diffusion_rs_b200 import ops
     B, T, D = 2, 300, 3072
