@@ -297,7 +297,7 @@ def run_ours(args):
     if gemm.get("launches"):
         ach = gemm["flops"] / (gemm["ms"] / 1e3) / 1e12
         traffic = None
-        tj = ROOT / "profiles" / "r1_gemm_traffic.json"
+        tj = ROOT / "profiles" / "r1b_gemm_traffic.json"  # ncu --set full capture of this launch shape (profiles/)
         if tj.exists():
             traffic = json.loads(tj.read_text()).get("dram_bytes_per_launch")
         roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel", "achieved": ach,
