@@ -63,6 +63,22 @@ SIGNATURES = {
                                     c_void_p]),
     "fluxb200_vae_decode_packed_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
                                               C.c_uint64, c_void_p]),
+    # text encoders
+    "fluxb200_t5_create": (c_int, [c_void_p, C.POINTER(c_void_p)]),
+    "fluxb200_t5_destroy": (None, [c_void_p]),
+    "fluxb200_t5_load_weight": (c_int, [c_void_p, C.c_char_p, c_void_p, c_int, C.POINTER(c_int64), c_int, c_int,
+                                        c_void_p]),
+    "fluxb200_t5_finalize": (c_int, [c_void_p, c_void_p]),
+    "fluxb200_t5_workspace_size": (c_int, [c_void_p, c_int, c_int, C.POINTER(C.c_uint64)]),
+    "fluxb200_t5_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, C.c_uint64, c_void_p]),
+    "fluxb200_clip_create": (c_int, [c_void_p, C.POINTER(c_void_p)]),
+    "fluxb200_clip_destroy": (None, [c_void_p]),
+    "fluxb200_clip_load_weight": (c_int, [c_void_p, C.c_char_p, c_void_p, c_int, C.POINTER(c_int64), c_int, c_int,
+                                          c_void_p]),
+    "fluxb200_clip_finalize": (c_int, [c_void_p, c_void_p]),
+    "fluxb200_clip_workspace_size": (c_int, [c_void_p, c_int, c_int, C.POINTER(C.c_uint64)]),
+    "fluxb200_clip_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, C.c_uint64,
+                                      c_void_p]),
     "fluxb200_conv2d_nhwc": (c_int, [c_void_p] * 5 + [c_int] * 6 + [c_void_p]),
     "fluxb200_repack_conv_weight": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "fluxb200_set_flag": (c_int, [C.c_char_p, c_int]),
@@ -80,6 +96,17 @@ class VaeConfigC(C.Structure):
     _fields_ = [("latent_channels", c_int), ("out_channels", c_int), ("block_out_channels", c_int * 4),
                 ("layers_per_block", c_int), ("norm_num_groups", c_int), ("mid_block_add_attention", c_int),
                 ("scaling_factor", c_float), ("shift_factor", c_float)]
+
+
+class T5ConfigC(C.Structure):
+    _fields_ = [(n, c_int) for n in ("vocab_size", "d_model", "d_kv", "d_ff", "num_layers", "num_heads",
+                                     "relative_attention_num_buckets", "relative_attention_max_distance")] + [
+        ("layer_norm_epsilon", c_float)]
+
+
+class ClipConfigC(C.Structure):
+    _fields_ = [(n, c_int) for n in ("vocab_size", "projection_dim", "intermediate_size", "max_position_embeddings",
+                                     "num_hidden_layers", "num_attention_heads")]
 
 
 class FluxConfigC(C.Structure):

@@ -214,6 +214,52 @@ int fluxb200_groupnorm_nhwc(const void* x, const void* weight, const void* bias,
                             fluxb200_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Text encoders: what FluxPipeline::forward runs once per prompt before the denoising loop
+ * (pipelines/flux/mod.rs:236-262).  Token ids come from the caller (the tokenizers are not part of this library);
+ * weights are bf16 tensors under the checkpoint names the reference's VarBuilder resolves.  Same ownership rules as
+ * the model handles above: caller-owned ids / outputs / workspace, library-owned weight copies.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct fluxb200_t5 fluxb200_t5;
+typedef struct {
+  int32_t vocab_size, d_model, d_kv /* 64 */, d_ff, num_layers, num_heads;
+  int32_t relative_attention_num_buckets, relative_attention_max_distance;
+  float layer_norm_epsilon;
+} fluxb200_t5_config; /* == models/t5/mod.rs:75-93 T5Config (encoder, feed_forward_proj = "gated-gelu") */
+
+int fluxb200_t5_create(const fluxb200_t5_config* cfg, fluxb200_t5** out);
+void fluxb200_t5_destroy(fluxb200_t5* m);
+/* names: "shared.weight", "encoder.block.{i}.layer.0.SelfAttention.{q,k,v,o}.weight",
+ * "encoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight", "encoder.block.{i}.layer.{0,1}.layer_norm.weight",
+ * "encoder.block.{i}.layer.1.DenseReluDense.{wi_0,wi_1,wo}.weight", "encoder.final_layer_norm.weight" */
+int fluxb200_t5_load_weight(fluxb200_t5* m, const char* name, const void* data, int32_t dtype, const int64_t* shape,
+                            int32_t rank, int32_t is_device, fluxb200_stream_t stream);
+int fluxb200_t5_finalize(fluxb200_t5* m, fluxb200_stream_t stream);
+int fluxb200_t5_workspace_size(const fluxb200_t5* m, int32_t batch, int32_t seq_len, uint64_t* bytes);
+/* T5EncoderModel::forward (t5/mod.rs:659): ids int32 device [B, L] (L <= 512) -> out bf16 device [B, L, d_model]. */
+int fluxb200_t5_forward(fluxb200_t5* m, const int32_t* ids, void* out, int32_t batch, int32_t seq_len, void* workspace,
+                        uint64_t workspace_bytes, fluxb200_stream_t stream);
+
+typedef struct fluxb200_clip fluxb200_clip;
+typedef struct {
+  int32_t vocab_size, projection_dim /* hidden width, = heads * 64 */, intermediate_size, max_position_embeddings;
+  int32_t num_hidden_layers, num_attention_heads;
+} fluxb200_clip_config; /* == models/clip/text.rs:22-31 ClipTextConfig (hidden_act = quick_gelu) */
+
+int fluxb200_clip_create(const fluxb200_clip_config* cfg, fluxb200_clip** out);
+void fluxb200_clip_destroy(fluxb200_clip* m);
+/* names are relative to "text_model." : "embeddings.{token,position}_embedding.weight",
+ * "encoder.layers.{i}.{layer_norm1,layer_norm2}.{weight,bias}", "encoder.layers.{i}.self_attn.{q,k,v,out}_proj.{weight,bias}",
+ * "encoder.layers.{i}.mlp.{fc1,fc2}.{weight,bias}", "final_layer_norm.{weight,bias}" */
+int fluxb200_clip_load_weight(fluxb200_clip* m, const char* name, const void* data, int32_t dtype, const int64_t* shape,
+                              int32_t rank, int32_t is_device, fluxb200_stream_t stream);
+int fluxb200_clip_finalize(fluxb200_clip* m, fluxb200_stream_t stream);
+int fluxb200_clip_workspace_size(const fluxb200_clip* m, int32_t batch, int32_t seq_len, uint64_t* bytes);
+/* ClipTextTransformer (clip/text.rs:291-316): ids int32 device [B, L] -> hidden bf16 [B, L, D] (forward_with_mask, may be
+ * NULL) and pooled bf16 [B, D] = hidden at argmax(ids) (Module::forward, may be NULL). */
+int fluxb200_clip_forward(fluxb200_clip* m, const int32_t* ids, void* hidden_out, void* pooled_out, int32_t batch,
+                          int32_t seq_len, void* workspace, uint64_t workspace_bytes, fluxb200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Launch accounting and optional per-kernel-class CUDA-event timing (evidence for bench.py; the reference has
  * only tracing spans, models/flux/model.rs:240-453).  Timing is off by default and costs two event records per
  * launch when enabled.
