@@ -194,7 +194,8 @@ def run_ours(args):
     quant = args.quant
     t_load = time.perf_counter()
     pipe = Pipeline.load(ModelSource.synthetic("black-forest-labs/FLUX.1-dev", quant=quant, num_layers=args.layers,
-                                               num_single_layers=args.single_layers))
+                                               num_single_layers=args.single_layers,
+                                               text_encoders=args.text_encoders))
     torch.cuda.synchronize()
     t_load = time.perf_counter() - t_load
     params = DiffusionGenerationParams(height=args.height, width=args.width, num_steps=args.num_steps,
@@ -280,6 +281,29 @@ def run_ours(args):
     # ---- timed: e2e through Pipeline.forward with host buffers ----
     image_e2e()  # warm the pinned staging buffers
     ms_e2e = timed(image_e2e, args.steps)
+    # ---- optional: the text encoders in front of the hot path, full-size random-init T5-XXL +
+    #      CLIP-L: their own time per prompt batch, and the end-to-end number from TOKEN IDS instead of embeddings ----
+    text = None
+    if args.text_encoders:
+        from diffusion_rs_b200.pipeline import PromptTokens
+        gt = torch.Generator().manual_seed(77)
+        toks = [PromptTokens(torch.randint(1, 32000, (l_txt,), generator=gt), torch.randint(1, 49000, (77,), generator=gt))
+                for _ in range(world * B)]
+
+        def encoders_only():
+            pipe.encode_prompts(toks[rank * B:(rank + 1) * B])
+
+        def image_e2e_tokens():
+            return pipe.forward(toks, params, noise=all_noise)
+
+        encoders_only()
+        ms_enc = timed(encoders_only, 5) / 5
+        image_e2e_tokens()
+        ms_tok = timed(image_e2e_tokens, args.steps)
+        text = {"t5": "t5-v1_1-xxl encoder (24 layers, d_model 4096), L=%d" % l_txt, "clip": "CLIP-L text (12 layers), L=77",
+                "encoders_ms_per_prompt_batch": ms_enc,
+                "e2e_from_token_ids": {"value": args.steps * B * world / (ms_tok / 1e3), "unit": UNIT,
+                                       "ms_per_step": ms_tok / args.steps}}
     clocks = sampler.stop() if rank == 0 else None
 
     if rank != 0:
@@ -323,7 +347,7 @@ def run_ours(args):
                                                                  if cpu else None),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": int(launches), "clocks": clocks, "load_s": t_load,
+        "gpu_launches": int(launches), "clocks": clocks, "load_s": t_load, "text_encoders": text,
     }
     line["dit_ms_per_step"] = (ms_total / args.steps) / params.num_steps  # upper bound: includes the VAE share
     line["profiled_image_ms"] = ms_prof
@@ -348,6 +372,8 @@ def main():
     ap.add_argument("--single-layers", type=int, default=None, help="debug: reduced number of single blocks")
     ap.add_argument("--no-kernel-timing", dest="kernel_timing", action="store_false")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--text-encoders", action="store_true",
+                    help="also load full-size random-init T5-XXL + CLIP-L and report their time and the e2e number from token ids")
     ap.add_argument("--attn-variant", type=int, default=None, help="debug: attention kernel build (see attention.cu)")
     args = ap.parse_args()
     if args.impl == "reference":

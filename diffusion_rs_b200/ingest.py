@@ -123,3 +123,44 @@ def scheduler_config_from_json(j: dict):
     return SchedulerConfig(base_image_seq_len=j.get("base_image_seq_len", 256), base_shift=j.get("base_shift", 0.5),
                            max_image_seq_len=j.get("max_image_seq_len", 4096), max_shift=j.get("max_shift", 1.15),
                            shift=j.get("shift", 1.0), use_dynamic_shifting=bool(j.get("use_dynamic_shifting", False)))
+
+
+def load_text_components(loader):
+    """Optional: the text encoders + tokenizers of a FLUX snapshot (pipelines/flux/mod.rs:60-140): `text_encoder`
+    (CLIP, tensors under `text_model.`), `text_encoder_2` (T5), `tokenizer/{vocab.json,merges.txt}`,
+    `tokenizer_2/tokenizer.json`.  Returns None when the snapshot does not carry them."""
+    need = ("text_encoder/config.json", "text_encoder_2/config.json")
+    if not all(loader.exists(n) for n in need):
+        return None
+    ccfg = json.loads(loader.read("text_encoder/config.json"))
+    tcfg = json.loads(loader.read("text_encoder_2/config.json"))
+    clip = {k[len("text_model."):]: cast_policy(k, v) for k, v in _load_safetensors(loader, "text_encoder").items()
+            if k.startswith("text_model.") and not k.endswith("position_ids")}
+    t5 = {k: cast_policy(k, v) for k, v in _load_safetensors(loader, "text_encoder_2").items()
+          if k.startswith(("shared.", "encoder."))}
+    toks = None
+    if loader.exists("tokenizer_2/tokenizer.json") and loader.exists("tokenizer/vocab.json") and \
+            loader.exists("tokenizer/merges.txt"):
+        toks = {"t5": loader.read("tokenizer_2/tokenizer.json"), "clip_vocab": loader.read("tokenizer/vocab.json"),
+                "clip_merges": loader.read("tokenizer/merges.txt")}
+    return ccfg, clip, tcfg, t5, toks
+
+
+def clip_config_from_json(j: dict):
+    from .text_encoders import ClipTextConfig
+    if j.get("hidden_act", "quick_gelu") != "quick_gelu":
+        raise L.Fluxb200Error(f"unsupported CLIP activation {j.get('hidden_act')} (clip/text.rs:8-11 knows quick_gelu)")
+    return ClipTextConfig(vocab_size=j["vocab_size"], projection_dim=j["projection_dim"],
+                          intermediate_size=j["intermediate_size"], max_position_embeddings=j["max_position_embeddings"],
+                          num_hidden_layers=j["num_hidden_layers"], num_attention_heads=j["num_attention_heads"])
+
+
+def t5_config_from_json(j: dict):
+    from .text_encoders import T5Config
+    if j.get("feed_forward_proj", "gated-gelu") != "gated-gelu":
+        raise L.Fluxb200Error(f"unsupported T5 feed_forward_proj {j.get('feed_forward_proj')}")
+    return T5Config(vocab_size=j["vocab_size"], d_model=j["d_model"], d_kv=j["d_kv"], d_ff=j["d_ff"],
+                    num_layers=j["num_layers"], num_heads=j["num_heads"],
+                    relative_attention_num_buckets=j["relative_attention_num_buckets"],
+                    relative_attention_max_distance=j.get("relative_attention_max_distance", 128),
+                    layer_norm_epsilon=float(j["layer_norm_epsilon"]))

@@ -3,9 +3,10 @@
 (diffusion_rs_core/src/lib.rs:43-45, pipelines/mod.rs:23-33, 110-270; Python surface diffusion_rs_py/src/lib.rs).
 
 What is B200-native here is the denoising hot path (`FluxPipeline::forward`, pipelines/flux/mod.rs:225-335, from the
-noise latents to the u8 image).  The text encoders (T5-XXL / CLIP-L) are outside the hot path: a
-caller passes their outputs as `PromptEmbeds`; bare prompt strings are mapped to deterministic synthetic embeddings
-so the API stays runnable without weights or network.
+noise latents to the u8 image) and, as the first widening step, the two text encoders in front
+of it (T5 / CLIP, text_encoders.py).  A prompt is one of: `PromptEmbeds` (encoder outputs computed elsewhere),
+`PromptTokens` (token ids -> the encoders run on the GPU), or a string (tokenised when the snapshot ships its
+tokenizers, otherwise mapped to deterministic synthetic embeddings so the API stays runnable without weights or network).
 Multi-GPU: one process per GPU; prompts are sharded across ranks (independent trajectories — no per-step collective);
 the only NCCL traffic is the weight broadcast at load.
 """
@@ -19,6 +20,7 @@ from dataclasses import dataclass
 import torch
 
 from . import lib as L
+from .text_encoders import ClipTextConfig, ClipTextTransformer, T5Config, T5EncoderModel
 from .transformer import FluxConfig, FluxTransformer
 from .vae import AutoEncoderKl, VaeConfig
 
@@ -51,6 +53,11 @@ class ModelSource:  # diffusion_rs_common/src/model_source.rs:17-60
     vae: dict | None = None
     num_layers: int | None = None         # synthetic only: reduced depth for tests
     num_single_layers: int | None = None
+    text_encoders: bool = False           # synthetic: also build random-init T5-XXL + CLIP-L
+    t5: dict | None = None                # tensors: optional text encoder checkpoints + their configs
+    clip: dict | None = None
+    t5_config: T5Config | None = None
+    clip_config: ClipTextConfig | None = None
 
     @staticmethod
     def from_model_id(model_id: str) -> "ModelSource":
@@ -62,8 +69,8 @@ class ModelSource:  # diffusion_rs_common/src/model_source.rs:17-60
 
     @staticmethod
     def synthetic(model_id: str = "black-forest-labs/FLUX.1-dev", quant=None, num_layers=None,
-                  num_single_layers=None) -> "ModelSource":
-        return ModelSource("synthetic", model_id, quant, None, None, num_layers, num_single_layers)
+                  num_single_layers=None, text_encoders: bool = False) -> "ModelSource":
+        return ModelSource("synthetic", model_id, quant, None, None, num_layers, num_single_layers, text_encoders)
 
     @staticmethod
     def tensors(model_id: str, transformer: dict, vae: dict) -> "ModelSource":
@@ -84,6 +91,14 @@ class PromptEmbeds:
     """Output of the (out-of-scope) text encoders for one prompt: T5 `txt` [l_txt, 4096], CLIP pooled `vec` [768]."""
     txt: torch.Tensor
     vec: torch.Tensor
+
+
+@dataclass
+class PromptTokens:
+    """Token ids of one prompt: what the reference's tokenizers produce (flux/mod.rs:203-222).  `t5_ids` / `clip_ids`
+    are 1-D integer tensors; batches are padded with 0 to the longest prompt exactly like tokenize_and_pad."""
+    t5_ids: torch.Tensor
+    clip_ids: torch.Tensor
 
 
 @dataclass
@@ -154,8 +169,10 @@ NOISE_SEED = 299792458  # the reference seeds cuRAND with this constant (cuda_ba
 class Pipeline:
     """`diffusion_rs_core::Pipeline` (pipelines/mod.rs:110-270)."""
 
-    def __init__(self, transformer: FluxTransformer, vae: AutoEncoderKl, scheduler: SchedulerConfig, is_dev: bool):
+    def __init__(self, transformer: FluxTransformer, vae: AutoEncoderKl, scheduler: SchedulerConfig, is_dev: bool,
+                 t5: T5EncoderModel | None = None, clip: ClipTextTransformer | None = None, tokenizers=None):
         self.transformer, self.vae, self.scheduler, self.is_dev = transformer, vae, scheduler, is_dev
+        self.t5, self.clip, self.tokenizers = t5, clip, tokenizers
         self.max_batch = 4  # images per denoise call on one GPU
         self._pinned = {}
 
@@ -185,8 +202,21 @@ class Pipeline:
                 va.load_weight(name, bcast(t.cuda()))
             tr.finalize()
             va.finalize()
+            t5 = clip = toks = None
+            text = ingest.load_text_components(loader)
+            if text is not None:
+                ccfg, clip_t, t5cfg, t5_t, tok_bytes = text
+                clip = ClipTextTransformer(ingest.clip_config_from_json(ccfg))
+                for name, t in clip_t.items():
+                    clip.load_weight(name, bcast(t.cuda()))
+                clip.finalize()
+                t5 = T5EncoderModel(ingest.t5_config_from_json(t5cfg))
+                for name, t in t5_t.items():
+                    t5.load_weight(name, bcast(t.cuda()))
+                t5.finalize()
+                toks = cls._build_tokenizers(tok_bytes)
             torch.cuda.synchronize()
-            return cls(tr, va, sched, fcfg.guidance_embeds)
+            return cls(tr, va, sched, fcfg.guidance_embeds, t5, clip, toks)
         is_dev = "schnell" not in source.model_id.lower()
         fcfg = FluxConfig(guidance_embeds=is_dev)
         if source.num_layers is not None:
@@ -217,8 +247,26 @@ class Pipeline:
                 va.load_weight(name, bcast(t.cuda().to(torch.bfloat16)))
         tr.finalize()
         va.finalize()
+        t5 = clip = None
+        if source.kind == "synthetic" and source.text_encoders:
+            from . import synthetic as S
+            t5, clip = T5EncoderModel(T5Config()), ClipTextTransformer(ClipTextConfig())
+            for name, t in S.iter_t5_tensors(t5.cfg):
+                t5.load_weight(name, bcast(t))
+            for name, t in S.iter_clip_tensors(clip.cfg):
+                clip.load_weight(name, bcast(t))
+            t5.finalize()
+            clip.finalize()
+        elif source.kind == "tensors" and source.t5 is not None and source.clip is not None:
+            t5, clip = T5EncoderModel(source.t5_config), ClipTextTransformer(source.clip_config)
+            for name, t in source.t5.items():
+                t5.load_weight(name, bcast(t.cuda()))
+            for name, t in source.clip.items():
+                clip.load_weight(name, bcast(t.cuda()))
+            t5.finalize()
+            clip.finalize()
         torch.cuda.synchronize()
-        return cls(tr, va, sched, is_dev)
+        return cls(tr, va, sched, is_dev, t5, clip)
 
     # -- helpers ------------------------------------------------------------------------------------------------------
     def text_len(self) -> int:
@@ -229,6 +277,57 @@ class Pipeline:
         txt = torch.randn(self.text_len(), self.transformer.cfg.joint_attention_dim, generator=g).to(torch.bfloat16)
         vec = torch.randn(self.transformer.cfg.pooled_projection_dim, generator=g).to(torch.bfloat16)
         return PromptEmbeds(txt, vec)
+
+    @staticmethod
+    def _build_tokenizers(tok_bytes):
+        """tokenizer_2/tokenizer.json (T5) + tokenizer/{vocab.json,merges.txt} (CLIP BPE), flux/mod.rs:74-88."""
+        if tok_bytes is None:
+            return None
+        try:
+            import json as _json
+            import tempfile
+            from pathlib import Path
+            from tokenizers import Tokenizer
+            from tokenizers.models import BPE
+        except ImportError:
+            return None
+        t5_tok = Tokenizer.from_str(tok_bytes["t5"].decode())
+        with tempfile.TemporaryDirectory() as d:
+            (Path(d) / "vocab.json").write_bytes(tok_bytes["clip_vocab"])
+            (Path(d) / "merges.txt").write_bytes(tok_bytes["clip_merges"])
+            from transformers import CLIPTokenizer
+            clip_tok = CLIPTokenizer(str(Path(d) / "vocab.json"), str(Path(d) / "merges.txt"))
+        return {"t5": t5_tok, "clip": clip_tok}
+
+    def tokenize(self, prompt: str) -> PromptTokens:
+        if self.tokenizers is None:
+            raise L.Fluxb200Error("this pipeline was loaded without tokenizers; pass PromptTokens or PromptEmbeds")
+        t5_ids = self.tokenizers["t5"].encode(prompt, add_special_tokens=True).ids
+        clip_ids = self.tokenizers["clip"](prompt)["input_ids"]
+        return PromptTokens(torch.tensor(t5_ids), torch.tensor(clip_ids))
+
+    def encode_prompts(self, prompts: list[PromptTokens]) -> list[PromptEmbeds]:
+        """tokenize_and_pad + t5_model.forward + clip_model.forward (flux/mod.rs:236-268): device-resident embeddings."""
+        if self.t5 is None or self.clip is None:
+            raise L.Fluxb200Error("this pipeline was loaded without text encoders; pass PromptEmbeds")
+
+        def pad(seqs, min_len=0):
+            n = max(max(len(s) for s in seqs), min_len)
+            out = torch.zeros(len(seqs), n, dtype=torch.int32)
+            for i, s in enumerate(seqs):
+                out[i, :len(s)] = s.to(torch.int32)
+            return out
+
+        t5_ids = pad([p.t5_ids for p in prompts])
+        if not self.is_dev:  # schnell: pad to exactly 256, longer prompts are an error (flux/mod.rs:243-253)
+            if t5_ids.shape[1] > 256:
+                raise L.Fluxb200Error("T5 embedding length greater than 256, please shrink the prompt or use the -dev "
+                                      "(with guidance distillation) version.")
+            t5_ids = pad([p.t5_ids for p in prompts], 256)
+        clip_ids = pad([p.clip_ids for p in prompts])
+        txt = self.t5.forward(t5_ids)      # [N, L, 4096]
+        vec = self.clip.forward(clip_ids)  # [N, 768]
+        return [PromptEmbeds(txt[i], vec[i]) for i in range(len(prompts))]
 
     def _pin(self, key, shape, dtype):
         t = self._pinned.get(key)
@@ -241,10 +340,17 @@ class Pipeline:
     def forward(self, prompts, params: DiffusionGenerationParams, noise: torch.Tensor | None = None,
                 seed: int = NOISE_SEED) -> list[torch.Tensor]:
         """N prompts -> N images (HWC uint8 host tensors).  `prompts` are strings or PromptEmbeds."""
+        prompts = list(prompts)
+        if not prompts:
+            return []
+        if self.tokenizers is not None and self.t5 is not None:
+            prompts = [self.tokenize(p) if isinstance(p, str) else p for p in prompts]
+        tok_idx = [i for i, p in enumerate(prompts) if isinstance(p, PromptTokens)]
+        if tok_idx:
+            for i, e in zip(tok_idx, self.encode_prompts([prompts[i] for i in tok_idx])):
+                prompts[i] = e
         embeds = [p if isinstance(p, PromptEmbeds) else self.synthetic_embeds(p) for p in prompts]
         n = len(embeds)
-        if n == 0:
-            return []
         h, w = latent_hw(params.height, params.width)
         if noise is None:  # get_noise flux/sampling.rs:5-14 -> .to_dtype(bf16) flux/mod.rs:276
             noise = torch.randn(n, 16, h, w, generator=torch.Generator().manual_seed(seed), dtype=torch.float32)
@@ -270,12 +376,16 @@ class Pipeline:
         txt_h = self._pin("txt", (B, l_txt, embeds[0].txt.shape[1]), torch.bfloat16)
         vec_h = self._pin("vec", (B, embeds[0].vec.shape[0]), torch.bfloat16)
         img_h = self._pin("img", (B, l_img, 64), torch.bfloat16)
-        for i, e in enumerate(embeds):
-            txt_h[i].copy_(e.txt)
-            vec_h[i].copy_(e.vec)
+        if all(e.txt.is_cuda and e.vec.is_cuda for e in embeds):  # outputs of our own encoders: stay on the device
+            txt = torch.stack([e.txt for e in embeds]).contiguous()
+            vec = torch.stack([e.vec for e in embeds]).contiguous()
+        else:
+            for i, e in enumerate(embeds):
+                txt_h[i].copy_(e.txt)
+                vec_h[i].copy_(e.vec)
+            txt = txt_h.to("cuda", non_blocking=True)
+            vec = vec_h.to("cuda", non_blocking=True)
         img_h.copy_(patchify(noise))
-        txt = txt_h.to("cuda", non_blocking=True)
-        vec = vec_h.to("cuda", non_blocking=True)
         img = img_h.to("cuda", non_blocking=True)
         img_ids1, txt_ids1 = make_ids(h2, w2, l_txt)
         img_ids = img_ids1[None].repeat(B, 1, 1).contiguous().cuda()

@@ -105,3 +105,50 @@ def iter_vae_tensors(cfg, device="cuda"):
             yield from conv(f"{d}up_blocks.{lvl}.upsamplers.0.conv", block_in, block_in, 3)
     yield from norm(d + "conv_norm_out", ch[0])
     yield from conv(d + "conv_out", ch[0], cfg.out_channels, 3)
+
+
+def iter_t5_tensors(cfg, device="cuda"):
+    """Yield (name, bf16 tensor) for the T5 encoder (models/t5/mod.rs:645-657; 4.7e9 parameters for t5-v1_1-xxl)."""
+    inner = cfg.num_heads * cfg.d_kv
+    yield "shared.weight", _randn("shared.weight", (cfg.vocab_size, cfg.d_model), 1.0, device=device)
+    for i in range(cfg.num_layers):
+        p = f"encoder.block.{i}.layer."
+        for n, shp in (("q", (inner, cfg.d_model)), ("k", (inner, cfg.d_model)), ("v", (inner, cfg.d_model)),
+                       ("o", (cfg.d_model, inner))):
+            name = p + f"0.SelfAttention.{n}.weight"
+            yield name, _randn(name, shp, 1.0 / math.sqrt(shp[1]), device=device)
+        if i == 0:
+            name = p + "0.SelfAttention.relative_attention_bias.weight"
+            yield name, _randn(name, (cfg.relative_attention_num_buckets, cfg.num_heads), 0.5, device=device)
+        yield p + "0.layer_norm.weight", _randn(p + "0.layer_norm.weight", (cfg.d_model,), 0.02, 1.0, device=device)
+        for n, shp in (("wi_0", (cfg.d_ff, cfg.d_model)), ("wi_1", (cfg.d_ff, cfg.d_model)), ("wo", (cfg.d_model, cfg.d_ff))):
+            name = p + f"1.DenseReluDense.{n}.weight"
+            yield name, _randn(name, shp, 1.0 / math.sqrt(shp[1]), device=device)
+        yield p + "1.layer_norm.weight", _randn(p + "1.layer_norm.weight", (cfg.d_model,), 0.02, 1.0, device=device)
+    yield "encoder.final_layer_norm.weight", _randn("encoder.final_layer_norm.weight", (cfg.d_model,), 0.02, 1.0,
+                                                    device=device)
+
+
+def iter_clip_tensors(cfg, device="cuda"):
+    """Yield (name, bf16 tensor) for the CLIP text tower, names relative to `text_model.` (models/clip/text.rs:253-265)."""
+    D, I = cfg.projection_dim, cfg.intermediate_size
+    yield "embeddings.token_embedding.weight", _randn("clip.tok", (cfg.vocab_size, D), 0.5, device=device)
+    yield "embeddings.position_embedding.weight", _randn("clip.pos", (cfg.max_position_embeddings, D), 0.1, device=device)
+
+    def lin(name, o, i):
+        yield name + ".weight", _randn("clip." + name + ".w", (o, i), 1.0 / math.sqrt(i), device=device)
+        yield name + ".bias", _randn("clip." + name + ".b", (o,), 0.02, device=device)
+
+    def ln(name):
+        yield name + ".weight", _randn("clip." + name + ".w", (D,), 0.02, 1.0, device=device)
+        yield name + ".bias", _randn("clip." + name + ".b", (D,), 0.02, device=device)
+
+    for i in range(cfg.num_hidden_layers):
+        p = f"encoder.layers.{i}."
+        for n in ("q_proj", "k_proj", "v_proj", "out_proj"):
+            yield from lin(p + "self_attn." + n, D, D)
+        yield from ln(p + "layer_norm1")
+        yield from ln(p + "layer_norm2")
+        yield from lin(p + "mlp.fc1", I, D)
+        yield from lin(p + "mlp.fc2", D, I)
+    yield from ln("final_layer_norm")

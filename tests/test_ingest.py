@@ -73,6 +73,36 @@ def test_ingest_layout_and_dtype_policy(tmp_path, kind):
     assert set(t_va) == {"decoder.conv_in.weight"}  # the pipeline never encodes
 
 
+def test_ingest_text_components(tmp_path):
+    """text_encoder (CLIP, `text_model.` prefix stripped), text_encoder_2 (T5) and the tokenizer files of a snapshot."""
+    tr, va = _tiny_tensors()
+    root = tmp_path / "model"
+    _write_model_dir(root, tr, va)
+    loader = ingest.open_source("model_id", str(root))
+    assert ingest.load_text_components(loader) is None  # a snapshot without text encoders is fine
+    for d in ("text_encoder", "text_encoder_2", "tokenizer", "tokenizer_2"):
+        (root / d).mkdir()
+    ccfg = {"vocab_size": 100, "projection_dim": 64, "intermediate_size": 128, "max_position_embeddings": 77,
+            "num_hidden_layers": 1, "num_attention_heads": 1, "hidden_act": "quick_gelu"}
+    t5cfg = {"vocab_size": 100, "d_model": 64, "d_kv": 64, "d_ff": 256, "num_layers": 1, "num_heads": 1,
+             "relative_attention_num_buckets": 32, "layer_norm_epsilon": 1e-6, "feed_forward_proj": "gated-gelu"}
+    (root / "text_encoder" / "config.json").write_text(json.dumps(ccfg))
+    (root / "text_encoder_2" / "config.json").write_text(json.dumps(t5cfg))
+    save_file({"text_model.final_layer_norm.weight": torch.randn(64), "text_model.embeddings.position_ids":
+               torch.arange(77)[None].float(), "logit_scale": torch.randn(1)},
+              str(root / "text_encoder" / "model.safetensors"))
+    save_file({"shared.weight": torch.randn(100, 64), "encoder.final_layer_norm.weight": torch.randn(64).half(),
+               "decoder.junk": torch.randn(2)}, str(root / "text_encoder_2" / "model.safetensors"))
+    c, clip, t, t5, toks = ingest.load_text_components(ingest.open_source("model_id", str(root)))
+    assert set(clip) == {"final_layer_norm.weight"} and clip["final_layer_norm.weight"].dtype == torch.bfloat16
+    assert set(t5) == {"shared.weight", "encoder.final_layer_norm.weight"}
+    assert toks is None  # no tokenizer files yet
+    assert ingest.clip_config_from_json(c).projection_dim == 64
+    assert ingest.t5_config_from_json(t).relative_attention_max_distance == 128
+    with pytest.raises(L.Fluxb200Error):
+        ingest.t5_config_from_json({**t5cfg, "feed_forward_proj": "relu"})
+
+
 def test_ingest_rejects_other_pipelines(tmp_path):
     tr, va = _tiny_tensors()
     root = tmp_path / "sd"

@@ -96,3 +96,37 @@ def test_text_encoder_errors(fluxlib):
             m.load_weight(k, v.cuda())
     with pytest.raises(L.Fluxb200Error, match="missing tensor"):
         m.finalize()
+
+
+def test_pipeline_prompt_tokens_end_to_end(fluxlib):
+    """Pipeline.forward with PromptTokens (ids -> T5 + CLIP on the GPU -> denoise -> VAE) gives the same image as feeding
+    the encoders' outputs as PromptEmbeds, and the T5 padding rule of tokenize_and_pad (pad with 0 to the longest)."""
+    from diffusion_rs_b200.pipeline import (DiffusionGenerationParams, ModelSource, Pipeline, PromptEmbeds,
+                                            PromptTokens)
+    from diffusion_rs_b200.text_encoders import ClipTextConfig, T5Config
+    from oracle import flux as OF
+    from oracle import vae as OV
+    fcfg = OF.FluxConfig(num_layers=1, num_single_layers=1, guidance_embeds=True)
+    tcfg = T.T5Config(vocab_size=300, d_model=4096, d_kv=64, d_ff=256, num_layers=1, num_heads=2)
+    ccfg = T.ClipConfig(vocab_size=400, projection_dim=768, intermediate_size=256, max_position_embeddings=77,
+                        num_hidden_layers=1, num_attention_heads=12)
+    src = ModelSource.tensors("black-forest-labs/FLUX.1-dev", OF.make_weights(fcfg), OV.make_weights(OV.VaeConfig()))
+    src.num_layers, src.num_single_layers = 1, 1
+    src.t5, src.clip = T.t5_make_weights(tcfg), T.clip_make_weights(ccfg)
+    src.t5_config, src.clip_config = T5Config(**tcfg.__dict__), ClipTextConfig(**ccfg.__dict__)
+    pipe = Pipeline.load(src)
+    g = torch.Generator().manual_seed(9)
+    toks = [PromptTokens(torch.randint(1, 300, (20,), generator=g), torch.randint(1, 399, (9,), generator=g)),
+            PromptTokens(torch.randint(1, 300, (32,), generator=g), torch.randint(1, 399, (14,), generator=g))]
+    params = DiffusionGenerationParams(height=64, width=64, num_steps=2, guidance_scale=3.5)
+    a = pipe.forward(toks, params)
+    emb = pipe.encode_prompts(toks)
+    assert emb[0].txt.shape == (32, 4096) and emb[0].vec.shape == (768,)  # padded to the longest prompt of the batch
+    b = pipe.forward([PromptEmbeds(e.txt.cpu(), e.vec.cpu()) for e in emb], params)
+    assert len(a) == 2 and a[0].shape == (64, 64, 3)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    # the T5 output itself matches the oracle on the padded ids
+    ids = torch.zeros(2, 32, dtype=torch.int64)
+    ids[0, :20], ids[1] = toks[0].t5_ids, toks[1].t5_ids
+    ref = T.T5Oracle(tcfg, src.t5, O.REF).forward(ids)
+    assert _rel(torch.stack([e.txt for e in emb]), ref) < 1.5e-2
