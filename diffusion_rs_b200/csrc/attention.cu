@@ -21,6 +21,8 @@
 //  * the MMA-issuing warp must not lose issue slots to the softmax warps (highest warp id wins arbitration) and
 //    its operands must be uniform (no per-MMA R2UR/ELECT waterfall): 3480 -> 3250 clk.
 //  * the exp2 phase is MUFU-bound (16/clk/SM); a packed f32x2 degree-3 polynomial for every 4th pair: 3250 -> 3030.
+//  * two threads per row (RPT=2: half the TMEM load / max scan / exp2 work per thread) is correct but slower
+//    (3430-3640 clk): five warps per sub-partition slow the TMEM load and the max exchange costs more than it saves.
 //  * inside the DiT step (power-capped clocks) all of this is worth 844 -> 1006 TFLOP/s.
 #include "internal.h"
 #include "ptx.cuh"
@@ -533,9 +535,6 @@ static const AttnVariant kAttnVariants[] = {
     FB_ATTN_VARIANT(false, 4, 4, true, 1, "1 CTA, poly 1/4, P in 4 instalments"),
     FB_ATTN_VARIANT(true, 4, 1, true, 1, "CTA pair, poly 1/4"),
     FB_ATTN_VARIANT(false, 4, 1, true, 2, "1 CTA, 2 threads per row, poly 1/4"),
-    FB_ATTN_VARIANT(false, 3, 1, true, 2, "1 CTA, 2 threads per row, poly 1/3"),
-    FB_ATTN_VARIANT(true, 4, 1, true, 2, "CTA pair, 2 threads per row, poly 1/4"),
-    FB_ATTN_VARIANT(false, 4, 1, false, 2, "1 CTA, 2 threads per row, poly 1/4, no ping-pong"),
 };
 static constexpr int kNumAttnVariants = sizeof(kAttnVariants) / sizeof(kAttnVariants[0]);
 

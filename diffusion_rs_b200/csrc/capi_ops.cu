@@ -69,6 +69,11 @@ int fluxb200_debug_sdpa_trace(const void* q, const void* k, const void* v, void*
   return launch_attention(d, static_cast<cudaStream_t>(stream));
 }
 
+int fluxb200_debug_gemm_trace(void* trace) {
+  set_gemm_trace(static_cast<long long*>(trace));
+  return 0;
+}
+
 int fluxb200_layernorm_modulate(const void* x, const void* shift, const void* scale, int64_t mod_bstride, void* out,
                                 int32_t batch, int32_t rows_per_batch, int32_t dim, float eps,
                                 fluxb200_stream_t stream) {

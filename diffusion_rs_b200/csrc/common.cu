@@ -57,10 +57,17 @@ ProfScope::~ProfScope() {
   cudaEventRecord(g_prof_recs[slot].b, stream);
 }
 
-static int g_flag_qkrope = 1, g_flag_pair = -1, g_flag_fdq = 0, g_flag_attn = -1, g_flag_pdl = -1;
+static int g_flag_qkrope = 1, g_flag_pair = -1, g_flag_fdq = 0, g_flag_attn = -1, g_flag_pdl = -1, g_flag_cl4 = -1;
 int get_flag(const char* name) {
   if (!strcmp(name, "qkrope_fusion")) return g_flag_qkrope;
   if (!strcmp(name, "fused_dequant")) return g_flag_fdq;
+  if (!strcmp(name, "gemm_cl4")) {
+    if (g_flag_cl4 < 0) {
+      const char* e = getenv("FLUXB200_GEMM_CL4");
+      g_flag_cl4 = (e && e[0] == '1') ? 1 : 0;  // off by default: measured slower than CTA pairs
+    }
+    return g_flag_cl4;
+  }
   if (!strcmp(name, "pdl")) {
     if (g_flag_pdl < 0) {
       const char* e = getenv("FLUXB200_PDL");
@@ -194,6 +201,7 @@ int fluxb200_set_flag(const char* name, int value) {
   if (!strcmp(name, "fused_dequant")) { fb::g_flag_fdq = value ? 1 : 0; return 0; }
   if (!strcmp(name, "attn_variant")) { fb::g_flag_attn = value; return 0; }
   if (!strcmp(name, "pdl")) { fb::g_flag_pdl = value ? 1 : 0; return 0; }
+  if (!strcmp(name, "gemm_cl4")) { fb::g_flag_cl4 = value ? 1 : 0; return 0; }
   return fb::fail(std::string("set_flag: unknown flag ") + name);
 }
 void fluxb200_profile_enable(int on) {

@@ -33,13 +33,25 @@ static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
 // the dequant-producer warps expand into the stage's bf16 B tile.
 static constexpr int PK_BYTES = 8192;
 static constexpr int PK_AUX_OFF = 4096;  // second TMA box of a stage (absmax / Q4_K header) lands here
+// CL4 = a cluster of two CTA pairs stacked along M computes a 512x256 tile (EXPERIMENT, off by default: the
+// "gemm_cl4" flag).  Measured (scripts/gemm_trace.py): the MMA thread waits for TMA data 19-24 % of every tile.  In a
+// CL4 cluster the two pairs need the same W tile: each CTA fetches only a quarter of it (64 rows) and TMA-multicasts
+// it to its sibling in the other pair, which cuts the L2 reads by 25 %.  Result: bit-identical, but 8-27 % SLOWER - the
+// limit is what each SM can ingest (its own 32 KB per k-block, however many CTAs requested it), not what L2 can
+// serve, and only 33 clusters of 4 CTAs with 200 KB of shared memory are co-resident (132 of 148 SMs,
+// scripts/ubench/cluster_probe.cu).  Data-ready signalling: every CTA arms its OWN full barrier with
+// the 32 KB that land in its shared memory (own A, own B quarter, the sibling's B quarter); the non-leader CTA of a
+// pair relays its barrier to the leader's `peer_full`; a stage is free again once BOTH pairs have consumed it
+// (multicast commits from both leaders, empty barrier count 2).
 template <bool CTA2, bool QB = false>
 struct GemmCfg {
   static constexpr int B_ROWS = CTA2 ? BLOCK_N / 2 : BLOCK_N;
   static constexpr int B_BYTES = B_ROWS * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES + (QB ? PK_BYTES : 0);  // 32 (+8) KB (pair) / 48 KB (single)
+  // 6 stages: a 7th (it fits) changes nothing (scripts/gemm_trace.py) - the feed is bound by each SM's ~51 B/clk of
+  // achieved L2->SM ingest against the 64 B/clk a 128x256 tile needs at the MMA floor, not by bytes in flight.
   static constexpr int STAGES = QB ? 5 : (CTA2 ? 6 : 4);
-  static constexpr size_t SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 4096 /*code-pair LUTs*/;
+  static constexpr size_t SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + (QB ? 4096 : 0) /*code-pair LUTs*/;
 };
 static constexpr int GEMM_THREADS = 320;  // warp 0 TMA, warp 1 MMA, then epilogue (+ dequant producer) warps
 // dense B (TMA):      warps 2..9 = 8 epilogue warps
@@ -52,9 +64,10 @@ static constexpr int CONV_TH = 8, CONV_TW = 16;  // 8x16 output pixels = one 128
 struct alignas(64) GemmProblemDev {
   CUtensorMap tmap_a;
   CUtensorMap tmap_b;
+  CUtensorMap tmap_b4;  // CL4: 64-row boxes of W
   int M, N, K, num_kb;
   int tiles_m, tiles_n, tile_begin, tile_end;
-  int sched_m;  // scheduling units along M: tiles_m (single CTA) or ceil(tiles_m / 2) (CTA pair)
+  int sched_m;  // scheduling units along M: tiles_m (single CTA), ceil(tiles_m / 2) (CTA pair), ceil(tiles_m / 4) (CL4)
   int group_m;  // rasterisation: tiles are walked M-fastest inside groups of `group_m` M-units
   int conv, cH, cW, cC, c_chunks, ksize, tiles_h, tiles_w;
   bf16* out0;
@@ -86,6 +99,7 @@ struct GemmParams {
   GemmProblemDev p[MAX_PROBLEMS];
   int count;
   int total_tiles;
+  long long* trace;  // debug (fluxb200_debug_gemm_trace): per tile of scheduling unit 0, clock64 waits of the MMA thread
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -451,16 +465,21 @@ __device__ __forceinline__ void dequant_producer(const GemmParams& P, uint8_t* s
   }
 }
 
-template <bool CTA2, bool QB>
+template <bool CTA2, bool QB, bool CL4 = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams P) {
+  static_assert(!CL4 || (CTA2 && !QB), "CL4 is a pair-of-pairs build for dense weights");
   using Cfg = GemmCfg<CTA2, QB>;
   constexpr int EPI_WARPS = EpiCfg<QB>::WARPS;
   constexpr int DQ_WARPS = QB ? 4 : 0;  // arrivals on a full barrier: 1 (TMA expect_tx) + dequant warps (of both CTAs)
   constexpr int STAGES = Cfg::STAGES;
   constexpr int STAGE_BYTES = Cfg::STAGE_BYTES;
-  const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0;       // rank inside the CTA pair
-  const int unit_id = CTA2 ? (blockIdx.x >> 1) : blockIdx.x;    // tile-scheduling unit (CTA or CTA pair)
-  const int num_units = CTA2 ? (gridDim.x >> 1) : gridDim.x;
+  const uint32_t rank_cl = CTA2 ? cluster_ctarank() : 0;        // rank inside the cluster (0..1, CL4: 0..3)
+  const uint32_t cta_rank = rank_cl & 1;                        // rank inside the CTA pair
+  const uint32_t pair_id = CL4 ? (rank_cl >> 1) : 0;            // CL4: which of the two pairs of the cluster
+  const uint32_t leader_cl = rank_cl & ~1u;                     // cluster rank of this pair's leader CTA
+  constexpr int UNIT_CTAS = CL4 ? 4 : (CTA2 ? 2 : 1);
+  const int unit_id = blockIdx.x / UNIT_CTAS;                   // tile-scheduling unit (CTA, CTA pair or cluster of 4)
+  const int num_units = gridDim.x / UNIT_CTAS;
   extern __shared__ uint8_t smem_raw[];
   // 128B swizzle needs 1024-byte aligned tiles
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -469,7 +488,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   uint64_t* tmem_full = empty_bar + STAGES;  // [2]
   uint64_t* tmem_empty = tmem_full + 2;      // [2]
   uint64_t* pk_full = tmem_empty + 2;        // [STAGES] packed weights of the stage have landed (QB only)
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(pk_full + STAGES);
+  uint64_t* peer_full = pk_full + STAGES;    // [STAGES] CL4: the non-leader CTA's stage has landed (relayed arrival)
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(peer_full + STAGES);
   float2* lut2 = reinterpret_cast<float2*>(smem + STAGES * STAGE_BYTES + 256);  // [2][256] byte -> (hi, lo) code pairs
 
   const int warp = threadIdx.x >> 5;
@@ -482,8 +502,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     }
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1 + (CTA2 ? 2 : 1) * DQ_WARPS);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], CL4 ? 2 : 1);  // CL4: both pairs' MMAs must have consumed the stage
       mbar_init(&pk_full[s], 1);
+      mbar_init(&peer_full[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
@@ -517,7 +538,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       for (int t = unit_id; t < P.total_tiles; t += num_units) {
         TileCoord tc = decode_tile(P, t);
         const GemmProblemDev& p = P.p[tc.prob];
-        const int m_t = CTA2 ? 2 * tc.m_t + static_cast<int>(cta_rank) : tc.m_t;
+        const int m_t = UNIT_CTAS * tc.m_t + static_cast<int>(rank_cl);
         const int b_row0 = tc.n_t * BLOCK_N + (CTA2 ? static_cast<int>(cta_rank) * Cfg::B_ROWS : 0);
         int cn = 0, ch0 = 0, cw0 = 0;
         if (p.conv) {
@@ -567,7 +588,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
               tma_load_2d(pk + PK_AUX_OFF, &p.tmap_aux[mi], &pk_full[stage], (((kb * BLOCK_K) >> bs_shift) & ~3) * 4, r0);
             }
           }
-          if (CTA2) {
+          if (CL4) {
+            // own A tile + own quarter of W (multicast to the sibling CTA of the other pair, which sends us its quarter)
+            mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+            tma_load_2d(sa, &p.tmap_a, &full_bar[stage], a_c0, m_t * BLOCK_M);
+            const uint16_t mask = static_cast<uint16_t>((1u << cta_rank) | (1u << (cta_rank + 2)));
+            tma_load_2d_mcast(sb + pair_id * (Cfg::B_BYTES / 2), &p.tmap_b4, &full_bar[stage], b_c0,
+                              b_row0 + static_cast<int>(pair_id) * (Cfg::B_ROWS / 2), mask);
+          } else if (CTA2) {
             // both CTAs' bytes are credited to the leader's barrier; only the leader arms it
             const uint32_t bar = mapa_u32(smem_u32(&full_bar[stage]), 0);
             if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (QB ? A_BYTES : STAGE_BYTES));
@@ -589,21 +617,53 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     }
   } else if (warp == 1) {
     // ================= MMA issuer (single thread; in pair mode only the leader CTA issues) =================
+    if (CL4 && lane == 0 && cta_rank == 1) {
+      // relay: tell the pair's leader when this CTA's stage (A tile + its half of W) has landed
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = unit_id; t < P.total_tiles; t += num_units) {
+        const GemmProblemDev& p = P.p[decode_tile(P, t).prob];
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          // relaxed: the payload was written by the async proxy (TMA) into THIS CTA's shared memory and is read there by
+          // the tensor core; a release.cluster arrive per k-block would drain this thread's loads and flush L1 (~1 us)
+          mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(&peer_full[stage]), leader_cl));
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
     if (lane == 0 && cta_rank == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(CTA2 ? 2 * BLOCK_M : BLOCK_M, BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int t = unit_id; t < P.total_tiles; t += num_units) {
+      long long* const trace = (unit_id == 0) ? P.trace : nullptr;
+      int tile_no = 0;
+      for (int t = unit_id; t < P.total_tiles; t += num_units, ++tile_no) {
         TileCoord tc = decode_tile(P, t);
         const GemmProblemDev& p = P.p[tc.prob];
+        const long long c0 = trace ? clock64() : 0;
         if (CTA2) mbar_wait_cluster(&tmem_empty[acc], acc_phase ^ 1); else mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
+        const long long c1 = trace ? clock64() : 0;
+        long long full_wait = 0;
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
         for (int kb = 0; kb < p.num_kb; ++kb) {
-          if (CTA2) mbar_wait_cluster(&full_bar[stage], phase); else mbar_wait(&full_bar[stage], phase);
+          const long long w0 = trace ? clock64() : 0;
+          if (CL4) {
+            mbar_wait(&full_bar[stage], phase);
+            mbar_wait_cluster(&peer_full[stage], phase);
+          } else if (CTA2) {
+            mbar_wait_cluster(&full_bar[stage], phase);
+          } else {
+            mbar_wait(&full_bar[stage], phase);
+          }
           tc_fence_after();
+          if (trace) full_wait += clock64() - w0;
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
           const uint64_t da = umma_smem_desc_sw128(sa, 16, 1024);
           const uint64_t db = umma_smem_desc_sw128(sa + A_BYTES, 16, 1024);
@@ -614,14 +674,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
             else      umma_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
           }
           // frees the smem slot (in both CTAs) once these MMAs have read it
-          if (CTA2) tc_commit_2sm(&empty_bar[stage], 3); else tc_commit(&empty_bar[stage]);
+          if (CL4) tc_commit_2sm(&empty_bar[stage], 0xF);
+          else if (CTA2) tc_commit_2sm(&empty_bar[stage], 3);
+          else tc_commit(&empty_bar[stage]);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
         // accumulator complete -> epilogue warps (of both CTAs)
-        if (CTA2) tc_commit_2sm(&tmem_full[acc], 3); else tc_commit(&tmem_full[acc]);
+        if (CTA2) tc_commit_2sm(&tmem_full[acc], static_cast<uint16_t>(3u << leader_cl)); else tc_commit(&tmem_full[acc]);
+        if (trace && tile_no < 64) {
+          trace[tile_no * 4 + 0] = c0;                 // tile start
+          trace[tile_no * 4 + 1] = c1 - c0;            // waited for the epilogue to free the accumulator
+          trace[tile_no * 4 + 2] = full_wait;          // waited for TMA data, summed over the k-blocks
+          trace[tile_no * 4 + 3] = clock64() - c0;     // tile total (issue side)
+        }
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -640,7 +708,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     for (int t = unit_id; t < P.total_tiles; t += num_units) {
       TileCoord tc = decode_tile(P, t);
       const GemmProblemDev& p = P.p[tc.prob];
-      const int m_t = CTA2 ? 2 * tc.m_t + static_cast<int>(cta_rank) : tc.m_t;
+      const int m_t = UNIT_CTAS * tc.m_t + static_cast<int>(rank_cl);
       const int r = q * 32 + lane;  // row inside the tile == TMEM lane
       long long grow;
       bool valid;
@@ -715,7 +783,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (CTA2) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));  // the leader's MMA thread waits on it
+        if (CTA2) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), leader_cl));  // the leader's MMA thread waits on it
         else      mbar_arrive(&tmem_empty[acc]);
       }
       if (++acc == 2) {
@@ -736,6 +804,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+static long long* g_gemm_trace = nullptr;
+void set_gemm_trace(long long* buf) { g_gemm_trace = buf; }
+
 int launch_gemm(const GemmDesc* descs, int count, cudaStream_t stream) {
   FB_REQUIRE(count >= 1 && count <= MAX_PROBLEMS, "launch_gemm: 1..4 problems per launch");
   static_assert(sizeof(GemmParams) < 32000, "kernel parameter block too large");
@@ -748,6 +819,8 @@ int launch_gemm(const GemmDesc* descs, int count, cudaStream_t stream) {
                                        static_cast<int>(GemmCfg<true>::SMEM)));
     FB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(GemmCfg<true, true>::SMEM)));
+    FB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(GemmCfg<true>::SMEM)));
     attr_set = true;
   }
   use_pair = get_flag("gemm_pair") != 0;  // A/B switch (env FLUXB200_GEMM_SINGLE_CTA=1 or fluxb200_set_flag)
@@ -758,6 +831,29 @@ int launch_gemm(const GemmDesc* descs, int count, cudaStream_t stream) {
       FB_REQUIRE(descs[i].qb != nullptr && !descs[i].conv, "launch_gemm: quantised and dense problems cannot share a launch");
     use_pair = true;  // the fused-dequant producer exists for the CTA-pair kernel only
   }
+  // CL4 (pairs of pairs with W multicast): dense, non-conv problems whose M fills 512-row units without much padding
+  bool use_cl4 = use_pair && !quant_b && get_flag("gemm_cl4") != 0;
+  for (int i = 0; i < count && use_cl4; ++i) {
+    const int tiles_m = (descs[i].M + BLOCK_M - 1) / BLOCK_M;
+    const int padded = (tiles_m + 3) / 4 * 4;
+    if (descs[i].conv || (padded - tiles_m) * 32 > tiles_m) use_cl4 = false;
+  }
+  static int max_clusters4 = -1;  // co-resident clusters of 4 CTAs of this kernel (33 on a 148-SM B200)
+  if (use_cl4 && max_clusters4 < 0) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(4 * (num_sms() / 4)), cfg.blockDim = dim3(GEMM_THREADS), cfg.dynamicSmemBytes = GemmCfg<true>::SMEM;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 4, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, gemm_tcgen05_kernel<true, false, true>, &cfg) != cudaSuccess || n < 1) {
+      cudaGetLastError();
+      n = 0;
+    }
+    max_clusters4 = n;
+  }
+  if (use_cl4 && max_clusters4 < 1) use_cl4 = false;
   const int b_box_rows = use_pair ? GemmCfg<true>::B_ROWS : GemmCfg<false>::B_ROWS;
   GemmParams P;
   memset(&P, 0, sizeof(P));
@@ -838,9 +934,13 @@ int launch_gemm(const GemmDesc* descs, int count, cudaStream_t stream) {
       FB_REQUIRE(d.ldb % 8 == 0, "launch_gemm: ldb must be a multiple of 8");
       int rc = encode_tmap_2d(&p.tmap_b, d.w, d.K, d.N, static_cast<uint64_t>(d.ldb) * 2, BLOCK_K, b_box_rows);
       if (rc) return rc;
+      if (use_cl4) {
+        rc = encode_tmap_2d(&p.tmap_b4, d.w, d.K, d.N, static_cast<uint64_t>(d.ldb) * 2, BLOCK_K, GemmCfg<true>::B_ROWS / 2);
+        if (rc) return rc;
+      }
     }
     p.tiles_n = (d.N + BLOCK_N - 1) / BLOCK_N;
-    p.sched_m = use_pair ? (p.tiles_m + 1) / 2 : p.tiles_m;
+    p.sched_m = use_cl4 ? (p.tiles_m + 3) / 4 : (use_pair ? (p.tiles_m + 1) / 2 : p.tiles_m);
     // L2-aware rasterisation: when the whole A operand fits comfortably in the 126 MB L2 (activations of one DiT
     // block: 28 MB), walk all of M for a few N tiles at a time so that every weight panel is fetched from HBM once
     // (ncu: 650 MB -> ~algorithmic 360 MB of DRAM traffic for the 4608x21504x3072 launch); otherwise groups of 8.
@@ -887,6 +987,7 @@ int launch_gemm(const GemmDesc* descs, int count, cudaStream_t stream) {
     if (d.N % 8 == 0) FB_REQUIRE(d.ld0 % 8 == 0, "launch_gemm: ldo must be a multiple of 8");
   }
   P.total_tiles = tile;
+  P.trace = g_gemm_trace;
   double flops = 0, bytes = 0;
   for (int i = 0; i < count; ++i) {
     flops += 2.0 * descs[i].M * static_cast<double>(descs[i].N) * descs[i].K;
@@ -896,7 +997,10 @@ int launch_gemm(const GemmDesc* descs, int count, cudaStream_t stream) {
   ProfScope _ps(KK_GEMM, flops, bytes, stream);
   count_launch(KK_GEMM);
   const bool pdl = get_flag("pdl") != 0;
-  if (use_pair) {
+  if (use_cl4) {
+    FB_CHECK_CUDA(launch_ex(gemm_tcgen05_kernel<true, false, true>, dim3(4 * std::min(tile, max_clusters4)),
+                            dim3(GEMM_THREADS), GemmCfg<true>::SMEM, stream, 4, pdl, P));
+  } else if (use_pair) {
     const dim3 grid(2 * std::min(tile, num_sms() / 2));
     if (quant_b)
       FB_CHECK_CUDA(launch_ex(gemm_tcgen05_kernel<true, true>, grid, dim3(GEMM_THREADS), GemmCfg<true, true>::SMEM, stream,

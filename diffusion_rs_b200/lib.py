@@ -30,6 +30,7 @@ SIGNATURES = {
     "fluxb200_sdpa": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p]),
     "fluxb200_debug_sdpa_trace": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p,
                                           c_void_p]),
+    "fluxb200_debug_gemm_trace": (c_int, [c_void_p]),
     "fluxb200_layernorm_modulate": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int, c_int,
                                             c_float, c_void_p]),
     "fluxb200_qknorm_rope": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,

@@ -65,6 +65,11 @@ int fluxb200_sdpa(const void* q, const void* k, const void* v, void* out, int32_
 int fluxb200_debug_sdpa_trace(const void* q, const void* k, const void* v, void* out, int32_t B, int32_t H, int32_t L,
                               float scale, void* trace, fluxb200_stream_t stream);
 
+/* Debug/profiling: while `trace` (device buffer of 64*4 int64) is non-NULL, every fluxb200 GEMM launch records, for the
+ * first 64 tiles of scheduling unit 0, the MMA thread's clock64 waits {tile start, wait for a free accumulator, wait for
+ * TMA data, tile total}; used by scripts/gemm_trace.py only. */
+int fluxb200_debug_gemm_trace(void* trace);
+
 /* out = modulate(LayerNorm(x)) = (LN(x) * (1 + scale[b])) + shift[b]; x,out bf16 [B*rows, 3072].
  * Replaces nn::LayerNorm::forward + ModulationOut::scale_shift (model.rs:33-38, 217-221). */
 int fluxb200_layernorm_modulate(const void* x, const void* shift, const void* scale, int64_t mod_bstride, void* out,
