@@ -16,6 +16,8 @@
 // 4096-token image stream instead of leaving 2/3 of the SMs idle.
 #include <vector>
 
+#include <stdlib.h>
+
 #include "internal.h"
 #include <cuda_fp16.h>
 
@@ -1001,7 +1003,12 @@ int launch_gemm(const GemmDesc* descs, int count, cudaStream_t stream) {
     FB_CHECK_CUDA(launch_ex(gemm_tcgen05_kernel<true, false, true>, dim3(4 * std::min(tile, max_clusters4)),
                             dim3(GEMM_THREADS), GemmCfg<true>::SMEM, stream, 4, pdl, P));
   } else if (use_pair) {
-    const dim3 grid(2 * std::min(tile, num_sms() / 2));
+    static int max_units = -1;  // experiment knob: FLUXB200_GEMM_MAX_UNITS=37 runs the pair kernel on half of the SMs
+    if (max_units < 0) {
+      const char* e = getenv("FLUXB200_GEMM_MAX_UNITS");
+      max_units = e ? std::max(1, atoi(e)) : num_sms() / 2;
+    }
+    const dim3 grid(2 * std::min(tile, std::min(max_units, num_sms() / 2)));
     if (quant_b)
       FB_CHECK_CUDA(launch_ex(gemm_tcgen05_kernel<true, true>, grid, dim3(GEMM_THREADS), GemmCfg<true, true>::SMEM, stream,
                               2, pdl, P));
