@@ -26,6 +26,12 @@ NVCC_FLAGS = [
 ]
 
 
+def _flags() -> list[str]:
+    """NVCC_FLAGS plus opt-in debug instrumentation (FLUXB200_GEMM_TRACE=1: clock64 trace of the GEMM's MMA thread)."""
+    extra = ["-DFB_GEMM_TRACE=1"] if os.environ.get("FLUXB200_GEMM_TRACE") == "1" else []
+    return NVCC_FLAGS + extra
+
+
 def _nvcc() -> str:
     for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if cand and Path(cand).exists():
@@ -43,12 +49,12 @@ def _stamp() -> str:
                     list((PKG.parent / "include").glob("*.h"))):
         h.update(p.name.encode())
         h.update(p.read_bytes())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(_flags()).encode())
     return h.hexdigest()
 
 
 def _compile_one(nvcc: str, src: Path, obj: Path, log: Path) -> tuple[Path, int, str]:
-    cmd = [nvcc, *NVCC_FLAGS, "-I", str(PKG.parent / "include"), "-I", str(CSRC), "-c", str(src), "-o", str(obj)]
+    cmd = [nvcc, *_flags(), "-I", str(PKG.parent / "include"), "-I", str(CSRC), "-c", str(src), "-o", str(obj)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     log.write_text(r.stdout + r.stderr)
     return src, r.returncode, r.stdout + r.stderr

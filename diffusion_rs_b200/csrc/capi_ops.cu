@@ -70,8 +70,7 @@ int fluxb200_debug_sdpa_trace(const void* q, const void* k, const void* v, void*
 }
 
 int fluxb200_debug_gemm_trace(void* trace) {
-  set_gemm_trace(static_cast<long long*>(trace));
-  return 0;
+  return set_gemm_trace(static_cast<long long*>(trace));
 }
 
 int fluxb200_layernorm_modulate(const void* x, const void* shift, const void* scale, int64_t mod_bstride, void* out,

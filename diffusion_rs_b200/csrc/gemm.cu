@@ -23,6 +23,10 @@
 
 #include "ptx.cuh"
 
+#ifndef FB_GEMM_TRACE
+#define FB_GEMM_TRACE 0
+#endif
+
 namespace fb {
 
 static constexpr int BLOCK_M = 128;
@@ -643,7 +647,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+#if FB_GEMM_TRACE
       long long* const trace = (unit_id == 0) ? P.trace : nullptr;
+#else
+      constexpr long long* trace = nullptr;  // tracing is compiled out of production builds (FLUXB200_GEMM_TRACE=1 python -m ...build)
+#endif
       int tile_no = 0;
       for (int t = unit_id; t < P.total_tiles; t += num_units, ++tile_no) {
         TileCoord tc = decode_tile(P, t);
@@ -807,7 +815,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
 // host side
 // ------------------------------------------------------------------------------------------------
 static long long* g_gemm_trace = nullptr;
-void set_gemm_trace(long long* buf) { g_gemm_trace = buf; }
+int set_gemm_trace(long long* buf) {
+  if (buf != nullptr && !FB_GEMM_TRACE)
+    return fail("this libfluxb200.so was built without the GEMM trace (rebuild with FLUXB200_GEMM_TRACE=1)");
+  g_gemm_trace = buf;
+  return 0;
+}
 
 int launch_gemm(const GemmDesc* descs, int count, cudaStream_t stream) {
   FB_REQUIRE(count >= 1 && count <= MAX_PROBLEMS, "launch_gemm: 1..4 problems per launch");

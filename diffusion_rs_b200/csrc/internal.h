@@ -144,7 +144,7 @@ inline cudaError_t launch_ex(void (*kern)(KArgs...), dim3 grid, dim3 block, size
 int get_flag(const char* name);
 // One persistent launch over up to 4 problems (grouped): img + txt streams share the machine.
 int launch_gemm(const GemmDesc* descs, int count, cudaStream_t stream);
-void set_gemm_trace(long long* buf);  // debug: device buffer of 64*4 int64 written by scheduling unit 0, or nullptr
+int set_gemm_trace(long long* buf);  // debug: device buffer of 64*4 int64 written by scheduling unit 0, or nullptr
 
 // ---- tcgen05 flash attention: q,k,v [B,H,L,128] bf16 -> out rows [B, L, H*128] split at L_split ----
 struct AttnDesc {

@@ -67,7 +67,8 @@ int fluxb200_debug_sdpa_trace(const void* q, const void* k, const void* v, void*
 
 /* Debug/profiling: while `trace` (device buffer of 64*4 int64) is non-NULL, every fluxb200 GEMM launch records, for the
  * first 64 tiles of scheduling unit 0, the MMA thread's clock64 waits {tile start, wait for a free accumulator, wait for
- * TMA data, tile total}; used by scripts/gemm_trace.py only. */
+ * TMA data, tile total}; used by scripts/gemm_trace.py only.  Needs a library built with FLUXB200_GEMM_TRACE=1 (the
+ * instrumentation is compiled out of production builds); otherwise a non-NULL `trace` returns an error. */
 int fluxb200_debug_gemm_trace(void* trace);
 
 /* out = modulate(LayerNorm(x)) = (LN(x) * (1 + scale[b])) + shift[b]; x,out bf16 [B*rows, 3072].

@@ -1,4 +1,9 @@
-"""Where does the GEMM's MMA thread wait?  clock64 trace of scheduling unit 0 (fluxb200_debug_gemm_trace)."""
+"""Where does the GEMM's MMA thread wait?  clock64 trace of scheduling unit 0 (fluxb200_debug_gemm_trace).
+
+The instrumentation is compiled out of production builds: run as  FLUXB200_GEMM_TRACE=1 python scripts/gemm_trace.py
+(and rebuild without the variable afterwards)."""
+import os
+os.environ.setdefault("FLUXB200_GEMM_TRACE", "1")
 import math
 import sys
 from pathlib import Path
