@@ -46,39 +46,60 @@ __global__ void __launch_bounds__(128, 4) ln_modulate_kernel(const bf16* __restr
   uint4 u[VEC];  // the row stays packed in registers (48 regs) so that >= 5 blocks fit on an SM
 #pragma unroll
   for (int k = 0; k < VEC; ++k) u[k] = *reinterpret_cast<const uint4*>(xr + (k * 32 + lane) * 8);
-  float s = 0.f, s2 = 0.f;
+  // The kernel was instruction-bound (~15 instructions per element at 31 rows per SM), not memory-bound: both passes
+  // now run on packed pairs — f32x2 add/fma for the statistics and the normalisation, then the modulate chain in
+  // bf16x2 (an HMUL2/HADD2.BF16 is exactly "f32 op, round to nearest even", the reference's per-op rounding).
+  float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
 #pragma unroll
   for (int k = 0; k < VEC; ++k) {
-    float v[8];
-    unpack8(u[k], v);
+    const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      s += v[e];
-      s2 += v[e] * v[e];
+    for (int e = 0; e < 4; ++e) {
+      const float lo = bf_lo(w[e]), hi = bf_hi(w[e]);
+      asm("{\n\t.reg .b64 a, v;\n\tmov.b64 a, {%0, %1};\n\tmov.b64 v, {%2, %3};\n\tadd.rn.f32x2 a, a, v;\n\t"
+          "mov.b64 {%0, %1}, a;\n\t}"
+          : "+f"(s0), "+f"(s1)
+          : "f"(lo), "f"(hi));
+      asm("{\n\t.reg .b64 a, v;\n\tmov.b64 a, {%0, %1};\n\tmov.b64 v, {%2, %3};\n\tfma.rn.f32x2 a, v, v, a;\n\t"
+          "mov.b64 {%0, %1}, a;\n\t}"
+          : "+f"(q0), "+f"(q1)
+          : "f"(lo), "f"(hi));
     }
   }
-  s = warp_sum(s);
-  s2 = warp_sum(s2);
+  const float s = warp_sum(s0 + s1);
+  const float s2 = warp_sum(q0 + q1);
   const float mean = s / D;
   const float var = s2 / D - mean * mean;
   const float inv_std = 1.0f / sqrtf(var + eps);
+  const float nmean = -mean;
   const bf16* sh = shift + static_cast<long long>(b) * mod_bstride;
   const bf16* sc = scale + static_cast<long long>(b) * mod_bstride;
   bf16* orow = out + static_cast<long long>(row) * D;
+  const __nv_bfloat162 one2 = __float2bfloat162_rn(1.0f);
 #pragma unroll
   for (int k = 0; k < VEC; ++k) {
     const int c = (k * 32 + lane) * 8;
-    float v[8], fs[8], fc[8], o[8];
-    unpack8(u[k], v);
-    unpack8(*reinterpret_cast<const uint4*>(sh + c), fs);
-    unpack8(*reinterpret_cast<const uint4*>(sc + c), fc);
+    const uint4 fs = *reinterpret_cast<const uint4*>(sh + c);
+    const uint4 fc = *reinterpret_cast<const uint4*>(sc + c);
+    const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+    const uint32_t ws[4] = {fs.x, fs.y, fs.z, fs.w};
+    const uint32_t wc[4] = {fc.x, fc.y, fc.z, fc.w};
+    uint32_t o[4];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      float n = rbf((v[e] - mean) * inv_std);
-      float m = rbf(n * rbf(fc[e] + 1.0f));
-      o[e] = rbf(m + fs[e]);
+    for (int e = 0; e < 4; ++e) {
+      float y0 = bf_lo(w[e]), y1 = bf_hi(w[e]);
+      // (v - mean) * inv_std in f32, two roundings like the reference's fused kernel, on both lanes at once
+      asm("{\n\t.reg .b64 v, m, r;\n\tmov.b64 v, {%0, %1};\n\tmov.b64 m, {%2, %2};\n\tmov.b64 r, {%3, %3};\n\t"
+          "add.rn.f32x2 v, v, m;\n\tmul.rn.f32x2 v, v, r;\n\tmov.b64 {%0, %1}, v;\n\t}"
+          : "+f"(y0), "+f"(y1)
+          : "f"(nmean), "f"(inv_std));
+      const __nv_bfloat162 n2 = __floats2bfloat162_rn(y0, y1);                               // LN -> bf16
+      const __nv_bfloat162 sc1 = __hadd2_rn(*reinterpret_cast<const __nv_bfloat162*>(&wc[e]), one2);  // scale + 1 -> bf16
+      const __nv_bfloat162 m2 = __hmul2_rn(n2, sc1);                                           // * -> bf16
+      const __nv_bfloat162 o2 = __hadd2_rn(m2, *reinterpret_cast<const __nv_bfloat162*>(&ws[e]));  // + shift -> bf16
+      o[e] = *reinterpret_cast<const uint32_t*>(&o2);
     }
-    *reinterpret_cast<uint4*>(orow + c) = pack8(o);
+    *reinterpret_cast<uint4*>(orow + c) = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
 

@@ -114,6 +114,8 @@ struct GemmParams {
 // mantissas are exact in f32; sums are exact in f32 whenever the smaller addend can matter), so the chain runs on
 // packed bf16x2 registers with no conversions.
 // ------------------------------------------------------------------------------------------------
+// The _rn forms matter: nvcc contracts __hadd2(__hmul2(a, b), c) into one HFMA2.BF16 (a single rounding), which is not
+// what the reference computes (gate * x and + residual are two tensor ops, two roundings).
 typedef __nv_bfloat162 bf162;
 __device__ __forceinline__ bf162 as_bf162(uint32_t u) { return *reinterpret_cast<bf162*>(&u); }
 __device__ __forceinline__ uint32_t as_u32(bf162 v) { return *reinterpret_cast<uint32_t*>(&v); }
@@ -135,12 +137,12 @@ __device__ __forceinline__ float tanh_f32(float x) {
 __device__ __forceinline__ bf162 gelu_bf16x2(bf162 v) {
   const bf162 kHalf = bf162_const(0.5f), kOne = bf162_const(1.0f);
   const bf162 kC = bf162_const(0.79788456080286535587989211986876373f), kK = bf162_const(0.044715f);
-  const bf162 a = __hmul2(kHalf, v);
-  const bf162 p = __hadd2(kOne, __hmul2(__hmul2(kK, v), v));
-  const bf162 q = __hmul2(__hmul2(kC, v), p);
+  const bf162 a = __hmul2_rn(kHalf, v);
+  const bf162 p = __hadd2_rn(kOne, __hmul2_rn(__hmul2_rn(kK, v), v));
+  const bf162 q = __hmul2_rn(__hmul2_rn(kC, v), p);
   const float2 qf = __bfloat1622float2(q);
   const bf162 t = __floats2bfloat162_rn(tanh_f32(qf.x), tanh_f32(qf.y));
-  return __hmul2(a, __hadd2(kOne, t));
+  return __hmul2_rn(a, __hadd2_rn(kOne, t));
 }
 // scalar (slow-path) version, same arithmetic
 __device__ __forceinline__ float gelu_bf16_steps(float v) {
@@ -175,12 +177,12 @@ __device__ __forceinline__ void epi16(const uint32_t* acc, bf16* outp, const bf1
       v = __floats2bfloat162_rn(a0 + bf_lo(b[i]), a1 + bf_hi(b[i]));
     } else {
       v = __floats2bfloat162_rn(a0, a1);
-      if (BIAS == BIAS_AFTER_ROUND) v = __hadd2(v, as_bf162(b[i]));  // separate bf16 broadcast_add
+      if (BIAS == BIAS_AFTER_ROUND) v = __hadd2_rn(v, as_bf162(b[i]));  // separate bf16 broadcast_add
     }
-    if (EV == EV_ALPHA) v = __hmul2(v, alpha2);
+    if (EV == EV_ALPHA) v = __hmul2_rn(v, alpha2);
     if (EV == EV_GELU) v = gelu_bf16x2(v);
-    if (EV == EV_GATE_RES) v = __hmul2(as_bf162(g[i]), v);
-    if (EV == EV_GATE_RES || EV == EV_RES) v = __hadd2(as_bf162(r[i]), v);
+    if (EV == EV_GATE_RES) v = __hmul2_rn(as_bf162(g[i]), v);
+    if (EV == EV_GATE_RES || EV == EV_RES) v = __hadd2_rn(as_bf162(r[i]), v);
     o[i] = as_u32(v);
   }
   *reinterpret_cast<uint4*>(outp) = *reinterpret_cast<uint4*>(&o[0]);
@@ -239,7 +241,7 @@ __device__ __forceinline__ void epi_qkrope(const GemmProblemDev& p, uint32_t t_h
         v = __floats2bfloat162_rn(a0 + bf_lo(b[i]), a1 + bf_hi(b[i]));
       } else {
         v = __floats2bfloat162_rn(a0, a1);
-        if (p.bias_mode == BIAS_AFTER_ROUND) v = __hadd2(v, as_bf162(b[i]));
+        if (p.bias_mode == BIAS_AFTER_ROUND) v = __hadd2_rn(v, as_bf162(b[i]));
       }
       x[c * 8 + i] = as_u32(v);
       const float2 f = __bfloat1622float2(v);
@@ -273,7 +275,7 @@ __device__ __forceinline__ void epi_qkrope(const GemmProblemDev& p, uint32_t t_h
         const uint32_t yu = as_u32(y);
         const uint32_t y00 = __byte_perm(yu, yu, 0x1010), y11 = __byte_perm(yu, yu, 0x3232);
         const uint2 cs = pe[static_cast<long long>(i) * p.qk_L];  // cs.x = (cos, sin), cs.y = (-sin, cos)
-        x[i] = as_u32(__hadd2(__hmul2(as_bf162(cs.x), as_bf162(y00)), __hmul2(as_bf162(cs.y), as_bf162(y11))));
+        x[i] = as_u32(__hadd2_rn(__hmul2_rn(as_bf162(cs.x), as_bf162(y00)), __hmul2_rn(as_bf162(cs.y), as_bf162(y11))));
       }
     }
   }

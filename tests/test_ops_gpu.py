@@ -86,6 +86,12 @@ def test_linear_gate_residual(fluxlib):
     v = O.linear(x.float(), w.float(), b.float(), fused_bias=True)
     ref = O.rb(res.float() + O.rb(gate.float()[:, None, :] * v))
     assert _err(out, ref)[1] < 3e-3
+    # gate * x and + residual are two tensor ops in the reference (two roundings, model.rs:217-226): given the same
+    # pre-activation the epilogue must be bit-exact, i.e. not contracted into one fused multiply-add
+    pre_gpu = ops.linear(x, w, b, bias_mode=ops.BIAS_FUSED).float()
+    ref2 = O.rb(res.float() + O.rb(gate.float()[:, None, :] * pre_gpu))
+    mism = (out.float() != ref2).float().mean().item()
+    assert mism < 1e-3, mism
 
 
 @pytest.mark.parametrize("B,H,L", [(1, 2, 256), (1, 3, 512), (2, 2, 384), (1, 2, 1000), (1, 24, 4608)])
