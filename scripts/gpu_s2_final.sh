@@ -23,5 +23,5 @@ scripts/ubench/mma_rate > gpurun_out/ubench_mma_rate.txt 2>&1; tail -25 gpurun_o
 scripts/ubench/exp_rate > gpurun_out/ubench_exp_rate.txt 2>&1; cat gpurun_out/ubench_exp_rate.txt
 scripts/ubench/cluster_probe > gpurun_out/ubench_cluster_probe.txt 2>&1; cat gpurun_out/ubench_cluster_probe.txt
 echo "=== attention variants + trace"
-timeout 300 python scripts/attn_variants.py 0 1 2 3 4 5 2>&1 | tail -8 | cut -c1-330
+timeout 300 python scripts/attn_variants.py 0 1 2 3 4 2>&1 | tail -8 | cut -c1-330
 } 2>&1 | tee gpurun_out/s2_final.log
