@@ -12,8 +12,12 @@ the upper-bound truth used to judge whose rounding error is smaller).
 Pinning: the op-level functions are checked against the reference's own known-answer vectors in
 tests/test_oracle_golden.py (softmax / layer_norm / rms_norm: diffusion_rs_common/src/nn/tests/ops.rs:9-139,
 group_norm: nn/tests/group_norm.rs:33-105, conv2d: core/tests/conv_tests.rs:126-166, Q4_K round trip:
-core/tests/quantized_tests.rs:567-612).  At model level (FLUX step, VAE decode, bnb linears) the reference ships
-no test and no golden tensor: **parity unpinned** above the op level.
+core/tests/quantized_tests.rs:567-612).  At model level (FLUX step, VAE decode, text encoders) the reference ships
+no test and no golden tensor; there the oracle's f32 graph is pinned against independent implementations of the same
+networks instead (tests/test_flux_oracle_pin.py: the Black Forest Labs FLUX / autoencoder code vendored by torchtitan;
+tests/test_text_oracle.py: HuggingFace T5EncoderModel / CLIPTextModel).  The bf16 ROUNDING POINTS (where the reference
+rounds between ops) remain a restatement of the Rust source that nothing executable here can confirm: **parity
+unpinned** at that level.
 """
 from __future__ import annotations
 
