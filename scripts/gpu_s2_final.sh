@@ -19,6 +19,9 @@ timeout 900 python bench.py --steps 1 --warmup 3 --height 720 --width 1280 --no-
 echo "=== C5 slice q4k batch 4"
 timeout 900 python bench.py --steps 1 --warmup 2 --quant q4k --batch 4 --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/bench_s2_q4k_b4.json; python scripts/show_bench.py gpurun_out/bench_s2_q4k_b4.json | head -4
 echo "=== microbenchmarks"
+for b in mma_rate exp_rate cluster_probe; do
+  [ -x scripts/ubench/$b ] || nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -Idiffusion_rs_b200/csrc scripts/ubench/$b.cu -o scripts/ubench/$b
+done
 scripts/ubench/mma_rate > gpurun_out/ubench_mma_rate.txt 2>&1; tail -25 gpurun_out/ubench_mma_rate.txt
 scripts/ubench/exp_rate > gpurun_out/ubench_exp_rate.txt 2>&1; cat gpurun_out/ubench_exp_rate.txt
 scripts/ubench/cluster_probe > gpurun_out/ubench_cluster_probe.txt 2>&1; cat gpurun_out/ubench_cluster_probe.txt
