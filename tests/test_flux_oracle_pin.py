@@ -143,3 +143,30 @@ def test_vae_decoder_oracle_f32_matches_bfl_reference_implementation():
     assert got.shape == ref.shape == (1, 3, 64, 96)
     rel = ((got - ref).norm() / ref.norm()).item()
     assert rel < 2e-5, rel
+
+
+def test_sampler_helpers_match_bfl_reference_implementation():
+    """Scheduler (`calculate_shift` + `get_timesteps`, pipelines/scheduler.rs:22-51, flux/sampling.rs:70-80), latent
+    packing / unpacking (flux/sampling.rs:29-31, 61-68) and position ids (flux/sampling.rs:32-49) — both the oracle's and
+    the product's host-side mirrors — against the BFL helpers vendored by torchtitan."""
+    tt_s = pytest.importorskip("torchtitan.experiments.flux.sampling")
+    tt_u = pytest.importorskip("torchtitan.experiments.flux.utils")
+    from diffusion_rs_b200 import pipeline as PL
+    for l_img, steps in ((256, 4), (4096, 50), (3600, 28)):
+        ref = tt_s.get_schedule(steps, l_img, shift=True)
+        mu = OF.calculate_shift(l_img)
+        assert mu == PL.calculate_shift(l_img, 256, 4096, 0.5, 1.15)
+        for ts in (OF.get_timesteps(steps, mu), PL.SchedulerConfig().get_timesteps(steps, mu)):
+            assert len(ts) == steps + 1 and ts[0] == 1.0 and ts[-1] == 0.0
+            assert max(abs(a - b) for a, b in zip(ts, ref)) < 1e-6  # BFL evaluates the shift in f32
+    # schnell: no shift -> plain linspace(1, 0)
+    ref = tt_s.get_schedule(4, 256, shift=False)
+    assert max(abs(a - b) for a, b in zip(PL.SchedulerConfig(use_dynamic_shifting=False, shift=1.0).get_timesteps(4, None), ref)) < 1e-7
+    lat = torch.randn(2, 16, 8, 12, generator=torch.Generator().manual_seed(5))
+    packed = tt_u.pack_latents(lat)
+    assert torch.equal(OF.patchify(lat), packed) and torch.equal(PL.patchify(lat), packed)
+    assert torch.equal(OF.unpack(packed, 8 * 8, 12 * 8), tt_u.unpack_latents(packed, 8, 12))
+    ids_ref = tt_u.create_position_encoding_for_latents(1, 8, 12)[0]
+    assert torch.equal(OF.make_ids(4, 6, 5)[5:], ids_ref) and torch.equal(OF.make_ids(4, 6, 5)[:5], torch.zeros(5, 3))
+    img_ids, txt_ids = PL.make_ids(4, 6, 5, dtype=torch.float32)
+    assert torch.equal(img_ids, ids_ref) and torch.equal(txt_ids, torch.zeros(5, 3))
