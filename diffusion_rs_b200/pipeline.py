@@ -364,6 +364,12 @@ class Pipeline:
             images += self._generate(embeds[s:e], noise[s:e], params)
         return images
 
+    def forward_png(self, prompts, params: DiffusionGenerationParams, **kw) -> list[bytes]:
+        """What the reference's Python binding returns (`diffuse_rs.pyi`: `Pipeline.forward(...) -> list[bytes]`,
+        diffusion_rs_py/src/lib.rs:140-154): one PNG-encoded image per prompt of this rank's shard."""
+        from .image import encode_png
+        return [encode_png(im) for im in self.forward(prompts, params, **kw)]
+
     def _generate(self, embeds, noise, params) -> list[torch.Tensor]:
         B = len(embeds)
         l_txt = embeds[0].txt.shape[0]
