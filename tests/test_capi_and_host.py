@@ -34,6 +34,30 @@ def test_library_exports_every_declared_symbol(fluxlib):
     assert all(s in syms for s in ffi)
 
 
+def test_header_is_plain_c_and_links_from_c(tmp_path, fluxlib):
+    """The boundary is a C ABI: include/fluxb200.h must compile as C99 (no C++ or torch types in the signatures) and a
+    C program must link against libfluxb200.so and get an error string back (no GPU needed for that)."""
+    import shutil
+    import subprocess
+    from diffusion_rs_b200 import lib as L
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "t.c"
+    src.write_text('#include <stdio.h>\n#include "fluxb200.h"\n'
+                   'int main(void) {\n'
+                   '  int rc = fluxb200_set_flag("no_such_flag", 1);\n'
+                   '  printf("%d|%s|%d\\n", rc, fluxb200_last_error(), fluxb200_version());\n'
+                   '  return rc == 0;\n}\n')
+    exe = tmp_path / "t"
+    libdir = L.lib_path().parent
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", f"-I{ROOT / 'include'}", str(src), "-o", str(exe),
+                    f"-L{libdir}", "-lfluxb200", f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.strip()
+    rc, msg, ver = out.split("|")
+    assert int(rc) != 0 and "unknown flag" in msg and int(ver) >= 100
+
+
 def test_no_cpu_fallback_and_error_reporting(fluxlib):
     """Without a GPU every compute entry point must fail loudly with a message, never silently compute on the CPU."""
     if torch.cuda.is_available():
