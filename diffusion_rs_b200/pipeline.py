@@ -280,31 +280,31 @@ class Pipeline:
 
     @staticmethod
     def _build_tokenizers(tok_bytes):
-        """tokenizer_2/tokenizer.json (T5) + tokenizer/{vocab.json,merges.txt} (CLIP BPE), flux/mod.rs:74-88."""
+        """tokenizer_2/tokenizer.json (T5: `Tokenizer::from_bytes`, flux/mod.rs:82-88) and tokenizer/{vocab.json,
+        merges.txt} (CLIP: `load_bpe_tokenizer`, diffusion_rs_common/src/tokenizer.rs:7-23 — a BARE BPE model: no
+        normaliser, no pre-tokeniser, no BOS/EOS, merges read from line 2 on; mirrored as is)."""
         if tok_bytes is None:
             return None
         try:
             import json as _json
-            import tempfile
-            from pathlib import Path
             from tokenizers import Tokenizer
             from tokenizers.models import BPE
         except ImportError:
             return None
         t5_tok = Tokenizer.from_str(tok_bytes["t5"].decode())
-        with tempfile.TemporaryDirectory() as d:
-            (Path(d) / "vocab.json").write_bytes(tok_bytes["clip_vocab"])
-            (Path(d) / "merges.txt").write_bytes(tok_bytes["clip_merges"])
-            from transformers import CLIPTokenizer
-            clip_tok = CLIPTokenizer(str(Path(d) / "vocab.json"), str(Path(d) / "merges.txt"))
+        vocab = _json.loads(tok_bytes["clip_vocab"].decode())
+        merges = [tuple(x.split(" ")) for x in tok_bytes["clip_merges"].decode().split("\n")[1:]]
+        merges = [m for m in merges if len(m) == 2]
+        clip_tok = Tokenizer(BPE(vocab=vocab, merges=merges))
         return {"t5": t5_tok, "clip": clip_tok}
 
     def tokenize(self, prompt: str) -> PromptTokens:
+        """`tokenizer.encode_batch(prompts, true)` -> ids (flux/mod.rs:203-222)."""
         if self.tokenizers is None:
             raise L.Fluxb200Error("this pipeline was loaded without tokenizers; pass PromptTokens or PromptEmbeds")
         t5_ids = self.tokenizers["t5"].encode(prompt, add_special_tokens=True).ids
-        clip_ids = self.tokenizers["clip"](prompt)["input_ids"]
-        return PromptTokens(torch.tensor(t5_ids), torch.tensor(clip_ids))
+        clip_ids = self.tokenizers["clip"].encode(prompt, add_special_tokens=True).ids
+        return PromptTokens(torch.tensor(t5_ids, dtype=torch.int64), torch.tensor(clip_ids, dtype=torch.int64))
 
     def encode_prompts(self, prompts: list[PromptTokens]) -> list[PromptEmbeds]:
         """tokenize_and_pad + t5_model.forward + clip_model.forward (flux/mod.rs:236-268): device-resident embeddings."""

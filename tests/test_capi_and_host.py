@@ -178,3 +178,31 @@ def test_two_rank_gloo_sharding_and_weight_broadcast():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert got == [(0, 3, 1000.0), (3, 5, 1000.0)]
+
+
+def test_tokenizers_mirror_the_reference_construction():
+    """T5: Tokenizer::from_bytes(tokenizer_2/tokenizer.json); CLIP: a BARE BPE model from vocab.json + merges.txt
+    (diffusion_rs_common/src/tokenizer.rs:7-23) - no lower-casing, no BOS/EOS, first merges line skipped."""
+    tokenizers = pytest.importorskip("tokenizers")
+    import json
+    from tokenizers import Tokenizer, models, pre_tokenizers, processors
+    from diffusion_rs_b200.pipeline import Pipeline, PromptTokens
+    t5 = Tokenizer(models.WordLevel({"<pad>": 0, "</s>": 1, "<unk>": 2, "a": 3, "cat": 4}, unk_token="<unk>"))
+    t5.pre_tokenizer = pre_tokenizers.Whitespace()
+    t5.post_processor = processors.TemplateProcessing(single="$A </s>", special_tokens=[("</s>", 1)])
+    vocab = {"c": 0, "a": 1, "t": 2, " ": 3, "ca": 4, "cat": 5}
+    merges = "#version: 0.2\nc a\nca t\n"
+    toks = Pipeline._build_tokenizers({"t5": t5.to_str().encode(), "clip_vocab": json.dumps(vocab).encode(),
+                                       "clip_merges": merges.encode()})
+    pipe = Pipeline.__new__(Pipeline)  # host-side logic only: no GPU objects needed
+    pipe.tokenizers = toks
+    out = pipe.tokenize("a cat")
+    assert isinstance(out, PromptTokens)
+    assert out.t5_ids.tolist() == [3, 4, 1]          # words + the </s> the T5 post-processor appends
+    assert out.clip_ids.tolist() == [1, 3, 5]        # bare BPE: 'a', ' ', 'cat' - no BOS/EOS, no </w> handling
+    ref = Tokenizer(models.BPE(vocab=vocab, merges=[("c", "a"), ("ca", "t")]))
+    assert out.clip_ids.tolist() == ref.encode("a cat", add_special_tokens=True).ids
+    pipe.tokenizers = None
+    from diffusion_rs_b200 import lib as L
+    with pytest.raises(L.Fluxb200Error):
+        pipe.tokenize("a cat")
