@@ -133,3 +133,47 @@ def test_pipeline_load_from_local_directory(tmp_path, fluxlib):
     b = p2.forward(["a cat"], params)
     assert a[0].shape == (64, 96, 3) and a[0].dtype == torch.uint8
     assert torch.equal(a[0], b[0])
+
+
+@pytest.mark.gpu
+def test_pipeline_from_snapshot_with_text_encoders_and_tokenizers(tmp_path, fluxlib):
+    """A local snapshot that ships text_encoder / text_encoder_2 / tokenizer / tokenizer_2: string prompts are tokenised
+    like the reference does, encoded by T5 + CLIP on the GPU and turned into images; the result equals feeding the same
+    token ids explicitly."""
+    pytest.importorskip("tokenizers")
+    from tokenizers import Tokenizer, models, pre_tokenizers, processors
+    from diffusion_rs_b200.pipeline import DiffusionGenerationParams, ModelSource, Pipeline, PromptTokens
+    from oracle import flux as OF
+    from oracle import text as OT
+    from oracle import vae as OV
+    cfg = OF.FluxConfig(num_layers=1, num_single_layers=1, guidance_embeds=True)
+    root = tmp_path / "flux"
+    _write_model_dir(root, OF.make_weights(cfg), OV.make_weights(OV.VaeConfig()))
+    for d in ("text_encoder", "text_encoder_2", "tokenizer", "tokenizer_2"):
+        (root / d).mkdir()
+    ccfg = OT.ClipConfig(vocab_size=16, projection_dim=768, intermediate_size=256, max_position_embeddings=77,
+                         num_hidden_layers=1, num_attention_heads=12)
+    tcfg = OT.T5Config(vocab_size=16, d_model=4096, d_kv=64, d_ff=256, num_layers=1, num_heads=2)
+    (root / "text_encoder" / "config.json").write_text(json.dumps({**ccfg.__dict__, "hidden_act": "quick_gelu"}))
+    (root / "text_encoder_2" / "config.json").write_text(json.dumps({**tcfg.__dict__, "feed_forward_proj": "gated-gelu"}))
+    save_file({"text_model." + k: v for k, v in OT.clip_make_weights(ccfg).items()},
+              str(root / "text_encoder" / "model.safetensors"))
+    save_file(OT.t5_make_weights(tcfg), str(root / "text_encoder_2" / "model.safetensors"))
+    t5 = Tokenizer(models.WordLevel({"<pad>": 0, "</s>": 1, "<unk>": 2, "a": 3, "cat": 4, "photo": 5, "of": 6},
+                                    unk_token="<unk>"))
+    t5.pre_tokenizer = pre_tokenizers.Whitespace()
+    t5.post_processor = processors.TemplateProcessing(single="$A </s>", special_tokens=[("</s>", 1)])
+    (root / "tokenizer_2" / "tokenizer.json").write_text(t5.to_str())
+    vocab = {"c": 0, "a": 1, "t": 2, " ": 3, "ca": 4, "cat": 5, "p": 6, "h": 7, "o": 8, "f": 9}
+    (root / "tokenizer" / "vocab.json").write_text(json.dumps(vocab))
+    (root / "tokenizer" / "merges.txt").write_text("#version: 0.2\nc a\nca t\n")
+    pipe = Pipeline.load(ModelSource.from_model_id(str(root)))
+    assert pipe.t5 is not None and pipe.clip is not None and pipe.tokenizers is not None
+    params = DiffusionGenerationParams(height=64, width=64, num_steps=2, guidance_scale=3.5)
+    a = pipe.forward(["a photo of a cat"], params)
+    toks = pipe.tokenize("a photo of a cat")
+    assert toks.t5_ids.tolist() == [3, 5, 6, 3, 4, 1]
+    b = pipe.forward([PromptTokens(toks.t5_ids, toks.clip_ids)], params)
+    assert a[0].shape == (64, 64, 3) and torch.equal(a[0], b[0])
+    png = pipe.forward_png(["a photo of a cat"], params)
+    assert png[0][:8] == b"\x89PNG\r\n\x1a\n"
