@@ -82,7 +82,7 @@ class ClockSampler:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
-        sm, mx, reasons = [], None, set()
+        sm, mx, reasons, power = [], None, set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
@@ -93,6 +93,10 @@ class ClockSampler:
                 mx = float(f[2])
             except ValueError:
                 continue
+            try:
+                power.append(float(f[3]))
+            except ValueError:
+                pass
             for n, v in zip(names, f[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
@@ -100,7 +104,11 @@ class ClockSampler:
         # "under load": drop the idle tail by taking the median of the upper half
         load = sm[len(sm) // 2:] if sm else []
         med = load[len(load) // 2] if load else None
-        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        power.sort()
+        # the loop is power-capped (sw_power_cap): joules per image = power x seconds per image is what to optimise
+        pw = power[len(power) // 2:] if power else []
+        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm),
+                "power_w": (pw[len(pw) // 2] if pw else None)}
 
 
 # ----------------------------------------------------------------------------------------------------------------------
