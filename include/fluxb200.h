@@ -270,10 +270,15 @@ int fluxb200_clip_forward(fluxb200_clip* m, const int32_t* ids, void* hidden_out
  * only tracing spans, models/flux/model.rs:240-453).  Timing is off by default and costs two event records per
  * launch when enabled.
  * ---------------------------------------------------------------------------------------------- */
-/* Runtime switches for A/B testing: "qkrope_fusion" (QK-norm + RoPE fused into the q|k|v GEMM epilogue, default 1),
- * "gemm_pair" (cta_group::2 GEMM, default 1), "fused_dequant" (model path: quantised weights expanded inside the GEMM's
- * operand producer instead of through an L2-sized bf16 staging buffer; default 0 because at M = 4608 tokens per weight
- * the staged path is faster). */
+/* Runtime switches for A/B testing (each also has an environment variable read at first use):
+ *   "qkrope_fusion"  QK-norm + RoPE fused into the q|k|v GEMM epilogue (default 1)
+ *   "gemm_pair"      cta_group::2 GEMM (default 1; FLUXB200_GEMM_SINGLE_CTA=1 turns it off)
+ *   "gemm_cl4"       cluster-of-4 GEMM with W multicast (default 0: measured slower; FLUXB200_GEMM_CL4=1)
+ *   "fused_dequant"  model path: quantised weights expanded inside the GEMM's operand producer instead of through an
+ *                    L2-sized bf16 staging buffer (default 0: at M = 4608 tokens per weight the staged path is faster)
+ *   "attn_variant"   build of the attention kernel, see attention.cu (default 0; FLUXB200_ATTN_VARIANT=n)
+ *   "pdl"            programmatic dependent launch for GEMM / attention / LN-modulate (default 1; FLUXB200_PDL=0)
+ * FLUXB200_GEMM_MAX_UNITS=n limits the pair GEMM to n CTA pairs (experiments only). */
 int fluxb200_set_flag(const char* name, int value);
 void fluxb200_profile_enable(int on);
 int fluxb200_profile_kinds(void);
