@@ -195,7 +195,7 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
     from diffusion_rs_b200.pipeline import (DiffusionGenerationParams, ModelSource, Pipeline, PromptEmbeds,
-                                            calculate_shift, latent_hw, make_ids, patchify)
+                                            calculate_shift, latent_hw, make_ids, patchify, shift_seq_len)
     lib = L.load()
     if args.attn_variant is not None:  # A/B switch for kernel experiments (scripts/); the default build is variant 0
         L.check(lib.fluxb200_set_flag(b"attn_variant", args.attn_variant))
@@ -229,7 +229,9 @@ def run_ours(args):
     img_ids = img_ids1[None].repeat(B, 1, 1).contiguous().cuda()
     txt_ids = txt_ids1[None].repeat(B, 1, 1).contiguous().cuda()
     sc = pipe.scheduler
-    mu = calculate_shift(l_img, sc.base_image_seq_len, sc.max_image_seq_len, sc.base_shift, sc.max_shift)
+    # the reference's call site passes the latent channel count (flux/mod.rs:279), mirrored by Pipeline.forward too
+    mu = calculate_shift(shift_seq_len(all_noise.shape, pipe.shift_mode), sc.base_image_seq_len, sc.max_image_seq_len,
+                         sc.base_shift, sc.max_shift)
     timesteps = sc.get_timesteps(params.num_steps, mu)
     out_u8 = torch.empty(B, 16 * h2, 16 * w2, 3, dtype=torch.uint8, device="cuda")
 

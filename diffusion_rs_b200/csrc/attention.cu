@@ -538,21 +538,26 @@ static const AttnVariant kAttnVariants[] = {
 };
 static constexpr int kNumAttnVariants = sizeof(kAttnVariants) / sizeof(kAttnVariants[0]);
 
+int attention_init_device() {
+  static DeviceOnce attr_once;
+  if (attr_once.need()) {
+    for (int i = 0; i < kNumAttnVariants; ++i) {
+      const int bytes = static_cast<int>(kAttnVariants[i].pair ? AttnCfg<true>::SMEM : AttnCfg<false>::SMEM);
+      FB_CHECK_CUDA(cudaFuncSetAttribute(kAttnVariants[i].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      FB_CHECK_CUDA(cudaFuncSetAttribute(kAttnVariants[i].fn_traced, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    }
+    attr_once.done();
+  }
+  return 0;
+}
+
 int launch_attention(const AttnDesc& d, cudaStream_t stream) {
   FB_REQUIRE(d.q && d.k && d.v, "attention: null q/k/v");
   FB_REQUIRE(d.B > 0 && d.H > 0 && d.L > 0, "attention: empty problem");
   FB_REQUIRE(d.l_split >= 0 && d.l_split <= d.L, "attention: bad l_split");
   FB_REQUIRE(d.l_split == 0 || d.out_a != nullptr, "attention: out_a required when l_split > 0");
   FB_REQUIRE(d.l_split == d.L || d.out_b != nullptr, "attention: out_b required");
-  static bool attr_set = false;
-  if (!attr_set) {
-    for (int i = 0; i < kNumAttnVariants; ++i) {
-      const int bytes = static_cast<int>(kAttnVariants[i].pair ? AttnCfg<true>::SMEM : AttnCfg<false>::SMEM);
-      FB_CHECK_CUDA(cudaFuncSetAttribute(kAttnVariants[i].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-      FB_CHECK_CUDA(cudaFuncSetAttribute(kAttnVariants[i].fn_traced, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    }
-    attr_set = true;
-  }
+  if (int rc = attention_init_device()) return rc;
   const int variant = get_flag("attn_variant");
   FB_REQUIRE(variant >= 0 && variant < kNumAttnVariants, "attention: unknown attn_variant");
   const bool pair = kAttnVariants[variant].pair != 0;

@@ -35,9 +35,30 @@ static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_pool;
 static unsigned long long g_launches[KK_COUNT] = {0};
 
 void count_launch(int kind, int n) { __atomic_fetch_add(&g_launches[kind], static_cast<unsigned long long>(n), __ATOMIC_RELAXED); }
+void count_launch_bulk(const unsigned long long* per_kind, int sign) {
+  for (int k = 0; k < KK_COUNT; ++k) {
+    if (sign >= 0) __atomic_fetch_add(&g_launches[k], per_kind[k], __ATOMIC_RELAXED);
+    else           __atomic_fetch_sub(&g_launches[k], per_kind[k], __ATOMIC_RELAXED);
+  }
+}
+void snapshot_launches(unsigned long long* per_kind) {
+  for (int k = 0; k < KK_COUNT; ++k) per_kind[k] = __atomic_load_n(&g_launches[k], __ATOMIC_RELAXED);
+}
+bool profiling_enabled() { return __atomic_load_n(&g_prof_on, __ATOMIC_RELAXED); }
+
+bool DeviceOnce::need() const {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+  return ((__atomic_load_n(&mask, __ATOMIC_ACQUIRE) >> dev) & 1ull) == 0;
+}
+void DeviceOnce::done() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;
+  __atomic_fetch_or(&mask, 1ull << dev, __ATOMIC_RELEASE);
+}
 
 ProfScope::ProfScope(int k, double flops, double bytes, cudaStream_t st) : kind(k), stream(st), slot(-1) {
-  if (!g_prof_on) return;
+  if (!profiling_enabled()) return;
   std::lock_guard<std::mutex> lk(g_prof_mu);
   ProfRec r;
   if (!g_prof_pool.empty()) {
@@ -57,7 +78,8 @@ ProfScope::~ProfScope() {
   cudaEventRecord(g_prof_recs[slot].b, stream);
 }
 
-static int g_flag_qkrope = 1, g_flag_pair = -1, g_flag_fdq = 0, g_flag_attn = -1, g_flag_pdl = -1, g_flag_cl4 = -1;
+static int g_flag_qkrope = 1, g_flag_pair = -1, g_flag_fdq = 0, g_flag_attn = -1, g_flag_pdl = -1, g_flag_cl4 = -1,
+           g_flag_graph = -1, g_flag_big = -1;
 int get_flag(const char* name) {
   if (!strcmp(name, "qkrope_fusion")) return g_flag_qkrope;
   if (!strcmp(name, "fused_dequant")) return g_flag_fdq;
@@ -67,6 +89,20 @@ int get_flag(const char* name) {
       g_flag_cl4 = (e && e[0] == '1') ? 1 : 0;  // off by default: measured slower than CTA pairs
     }
     return g_flag_cl4;
+  }
+  if (!strcmp(name, "step_graph")) {
+    if (g_flag_graph < 0) {
+      const char* e = getenv("FLUXB200_STEP_GRAPH");
+      g_flag_graph = (e && e[0] == '0') ? 0 : 1;
+    }
+    return g_flag_graph;
+  }
+  if (!strcmp(name, "gemm_big")) {
+    if (g_flag_big < 0) {
+      const char* e = getenv("FLUXB200_GEMM_BIG");
+      g_flag_big = e ? atoi(e) : 1;
+    }
+    return g_flag_big;
   }
   if (!strcmp(name, "pdl")) {
     if (g_flag_pdl < 0) {
@@ -202,11 +238,13 @@ int fluxb200_set_flag(const char* name, int value) {
   if (!strcmp(name, "attn_variant")) { fb::g_flag_attn = value; return 0; }
   if (!strcmp(name, "pdl")) { fb::g_flag_pdl = value ? 1 : 0; return 0; }
   if (!strcmp(name, "gemm_cl4")) { fb::g_flag_cl4 = value ? 1 : 0; return 0; }
+  if (!strcmp(name, "step_graph")) { fb::g_flag_graph = value ? 1 : 0; return 0; }
+  if (!strcmp(name, "gemm_big")) { fb::g_flag_big = value; return 0; }
   return fb::fail(std::string("set_flag: unknown flag ") + name);
 }
 void fluxb200_profile_enable(int on) {
   std::lock_guard<std::mutex> lk(fb::g_prof_mu);
-  fb::g_prof_on = on != 0;
+  __atomic_store_n(&fb::g_prof_on, on != 0, __ATOMIC_RELAXED);
 }
 // Synchronises the device, folds every recorded event pair into per-kind totals and clears the records.
 // Arrays must hold fluxb200_profile_kinds() entries. ms = summed kernel time, count = event pairs.
@@ -227,8 +265,8 @@ int fluxb200_profile_collect(double* ms, double* flops, double* bytes, unsigned 
 }
 int fluxb200_profile_kinds(void) { return fb::KK_COUNT; }
 const char* fluxb200_profile_kind_name(int k) {
-  static const char* names[] = {"gemm_tcgen05", "attention_tcgen05", "ln_modulate", "qknorm_rope", "gemv_jobs",
-                                "dequant", "groupnorm", "misc"};
+  static const char* names[] = {"gemm_tcgen05", "attention_tcgen05", "ln_modulate", "qknorm_rope", "dequant",
+                                "groupnorm", "misc"};
   return (k >= 0 && k < fb::KK_COUNT) ? names[k] : "?";
 }
 // Kernel launches issued by this library since load (all kinds / one kind).

@@ -33,7 +33,8 @@ __global__ void __launch_bounds__(128, 4) ln_modulate_kernel(const bf16* __restr
                                                           int in_row_off, int rows_per_batch, int total_rows,
                                                           const bf16* __restrict__ shift,
                                                           const bf16* __restrict__ scale, long long mod_bstride,
-                                                          bf16* __restrict__ out, float eps) {
+                                                          bf16* __restrict__ out, float eps,
+                                                          const int* __restrict__ step_ptr, long long step_stride) {
   constexpr int VEC = D / 256;  // uint4 (8 bf16) per lane
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 4 + warp;
@@ -72,8 +73,11 @@ __global__ void __launch_bounds__(128, 4) ln_modulate_kernel(const bf16* __restr
   const float var = s2 / D - mean * mean;
   const float inv_std = 1.0f / sqrtf(var + eps);
   const float nmean = -mean;
-  const bf16* sh = shift + static_cast<long long>(b) * mod_bstride;
-  const bf16* sc = scale + static_cast<long long>(b) * mod_bstride;
+  // denoising loop: the modulation vectors of ALL steps were projected before the loop ([step][batch][...]); the
+  // current step comes from a device counter so that one captured CUDA graph serves every step
+  const long long mod_off = static_cast<long long>(b) * mod_bstride + (step_ptr ? *step_ptr * step_stride : 0);
+  const bf16* sh = shift + mod_off;
+  const bf16* sc = scale + mod_off;
   bf16* orow = out + static_cast<long long>(row) * D;
   const __nv_bfloat162 one2 = __float2bfloat162_rn(1.0f);
 #pragma unroll
@@ -105,13 +109,14 @@ __global__ void __launch_bounds__(128, 4) ln_modulate_kernel(const bf16* __restr
 
 int launch_ln_modulate(const bf16* x, long long in_bstride_rows, int in_row_off, int rows_per_batch, int batch,
                        const bf16* shift, const bf16* scale, long long mod_bstride, bf16* out, int D, float eps,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, const int* step_ptr, long long step_stride) {
   FB_REQUIRE(D == 3072, "ln_modulate: hidden size must be 3072 (HIDDEN_SIZE, model.rs:17)");
   const int total = rows_per_batch * batch;
   ProfScope _ps(KK_LN_MOD, 0, 4.0 * total * D, stream);
   count_launch(KK_LN_MOD, 1);
   FB_CHECK_CUDA(launch_ex(ln_modulate_kernel<3072>, dim3((total + 3) / 4), dim3(128), 0, stream, 1, get_flag("pdl") != 0,
-                          x, in_bstride_rows, in_row_off, rows_per_batch, total, shift, scale, mod_bstride, out, eps));
+                          x, in_bstride_rows, in_row_off, rows_per_batch, total, shift, scale, mod_bstride, out, eps,
+                          step_ptr, step_stride));
   FB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -190,123 +195,7 @@ int launch_qknorm_rope(const bf16* qkv, long long ld, int rows_per_batch, int ba
 }
 
 // ------------------------------------------------------------------------------------------------
-// Batched skinny linears (M = batch <= 8): every AdaLN modulation projection of a step in ONE launch.
-//   out[b, n] = bf16( bf16( sum_k x[b,k] * W[n,k] ) + bias[n] )     (rank-2 path of UnquantLinear::forward,
-//   unquantized/mod.rs:67: matmul rounds to bf16, then a separate bf16 broadcast_add)
-// HBM-bound on the weights: one warp per output row streams W[n, :] once with 16-byte loads, x lives in smem.
-// ------------------------------------------------------------------------------------------------
-template <int BMAX>
-__global__ void __launch_bounds__(256) gemv_jobs_kernel(const GemvJob* __restrict__ jobs, int njobs, int row_base,
-                                                        int total_rows, const bf16* __restrict__ x, long long x_ld,
-                                                        int B, int K, bf16* __restrict__ out_base) {
-  extern __shared__ uint8_t smem_raw[];
-  bf16* xs = reinterpret_cast<bf16*>(smem_raw);  // [B][K]
-  for (int i = threadIdx.x; i < B * (K / 8); i += blockDim.x) {
-    const int b = i / (K / 8), c = i - b * (K / 8);
-    reinterpret_cast<uint4*>(xs)[i] = *reinterpret_cast<const uint4*>(x + b * x_ld + c * 8);
-  }
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int ROWS_PER_WARP = 4;
-  const int row0 = (blockIdx.x * 8 + warp) * ROWS_PER_WARP;
-  if (row0 >= total_rows) return;
-  // The kernel is HBM-bound (6.5 GB of modulation weights per DiT step): the warp's four rows are streamed together so
-  // that every lane keeps four independent 16-byte loads in flight per k-chunk (per-row arithmetic order unchanged).
-  GemvJob job[ROWS_PER_WARP];
-  const bf16* wr[ROWS_PER_WARP];
-  int nrow[ROWS_PER_WARP];
-  bool live[ROWS_PER_WARP];
-#pragma unroll
-  for (int rr = 0; rr < ROWS_PER_WARP; ++rr) {
-    live[rr] = row0 + rr < total_rows;
-    const int grow = row_base + (live[rr] ? row0 + rr : row0);
-    int lo = 0, hi = njobs - 1;  // last job with row_begin <= grow
-    while (lo < hi) {
-      const int mid = (lo + hi + 1) >> 1;
-      if (jobs[mid].row_begin <= grow) lo = mid; else hi = mid - 1;
-    }
-    job[rr] = jobs[lo];
-    nrow[rr] = grow - job[rr].row_begin;
-    wr[rr] = job[rr].w + static_cast<long long>(nrow[rr]) * K;
-  }
-  float acc[ROWS_PER_WARP][BMAX];
-#pragma unroll
-  for (int rr = 0; rr < ROWS_PER_WARP; ++rr)
-#pragma unroll
-    for (int b = 0; b < BMAX; ++b) acc[rr][b] = 0.f;
-  for (int c = lane; c < K / 8; c += 32) {
-    uint4 wv[ROWS_PER_WARP];
-#pragma unroll
-    for (int rr = 0; rr < ROWS_PER_WARP; ++rr) wv[rr] = *reinterpret_cast<const uint4*>(wr[rr] + c * 8);
-#pragma unroll
-    for (int b = 0; b < BMAX; ++b) {
-      if (b < B) {
-        float xf[8];
-        unpack8(reinterpret_cast<const uint4*>(xs + b * K)[c], xf);
-#pragma unroll
-        for (int rr = 0; rr < ROWS_PER_WARP; ++rr) {
-          float wf[8];
-          unpack8(wv[rr], wf);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) acc[rr][b] = fmaf(wf[e], xf[e], acc[rr][b]);
-        }
-      }
-    }
-  }
-#pragma unroll
-  for (int rr = 0; rr < ROWS_PER_WARP; ++rr) {
-#pragma unroll
-    for (int b = 0; b < BMAX; ++b) acc[rr][b] = warp_sum(acc[rr][b]);
-    if (lane == 0 && live[rr]) {
-      const int n = nrow[rr];
-      const float bias = job[rr].bias ? __bfloat162float(job[rr].bias[n]) : 0.f;
-#pragma unroll
-      for (int b = 0; b < BMAX; ++b) {
-        if (b < B) {
-          float v;
-          if (job[rr].bias && job[rr].fused_bias) {
-            v = rbf(acc[rr][b] + bias);
-          } else {
-            v = rbf(acc[rr][b]);
-            if (job[rr].bias) v = rbf(v + bias);
-          }
-          out_base[job[rr].out_off + b * job[rr].out_ld + n] = __float2bfloat16_rn(v);
-        }
-      }
-    }
-  }
-}
-
-int launch_gemv_jobs(const GemvJob* jobs_dev, int njobs, int row_base, int total_rows, const bf16* x, long long x_ld,
-                     int B, int K, bf16* out_base, cudaStream_t stream) {
-  FB_REQUIRE(B >= 1 && B <= 8, "gemv_jobs: batch must be in 1..8");
-  FB_REQUIRE(K % 8 == 0, "gemv_jobs: K must be a multiple of 8");
-  const size_t smem = static_cast<size_t>(B) * K * 2;
-  FB_REQUIRE(smem <= 96 * 1024, "gemv_jobs: batch*K too large for shared memory");
-  const int grid = (total_rows + 31) / 32;
-  ProfScope _ps(KK_GEMV, 2.0 * total_rows * K * B, 2.0 * total_rows * K, stream);
-  count_launch(KK_GEMV);
-  if (B <= 2) {
-    static bool set2 = false;
-    if (!set2) {
-      FB_CHECK_CUDA(cudaFuncSetAttribute(gemv_jobs_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-      set2 = true;
-    }
-    gemv_jobs_kernel<2><<<grid, 256, smem, stream>>>(jobs_dev, njobs, row_base, total_rows, x, x_ld, B, K, out_base);
-  } else {
-    static bool set8 = false;
-    if (!set8) {
-      FB_CHECK_CUDA(cudaFuncSetAttribute(gemv_jobs_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-      set8 = true;
-    }
-    gemv_jobs_kernel<8><<<grid, 256, smem, stream>>>(jobs_dev, njobs, row_base, total_rows, x, x_ld, B, K, out_base);
-  }
-  FB_CHECK_CUDA(cudaGetLastError());
-  return 0;
-}
-
-// ------------------------------------------------------------------------------------------------
-// small per-step kernels
+// small kernels of the per-image prologue (vec_ of every step) and of the step graph
 // ------------------------------------------------------------------------------------------------
 // SiLU in bf16 steps: v / (1 + exp(-v))  (core/op.rs:699-706)
 __global__ void silu_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, long long n) {
@@ -346,18 +235,75 @@ int launch_timestep_embedding(const float* t, bf16* out, int B, int dim, cudaStr
 }
 
 // vec_ = (a [+ g]) + y, each add rounded to bf16 (model.rs:813-820)
+// a: [rows, D] (one row per (step, batch element)); g, y: [B, D] (they do not depend on the step): row r uses g/y row r % B
 __global__ void vec_combine_kernel(const bf16* __restrict__ a, const bf16* __restrict__ g, const bf16* __restrict__ y,
-                                   bf16* __restrict__ out, int n) {
+                                   bf16* __restrict__ out, int rows, int B, int Dm) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  if (i >= rows * Dm) return;
+  const int r = i / Dm, c = i - r * Dm;
+  const int j = (r % B) * Dm + c;
   float v = __bfloat162float(a[i]);
-  if (g) v = rbf(v + __bfloat162float(g[i]));
-  v = rbf(v + __bfloat162float(y[i]));
+  if (g) v = rbf(v + __bfloat162float(g[j]));
+  v = rbf(v + __bfloat162float(y[j]));
   out[i] = __float2bfloat16_rn(v);
 }
-int launch_vec_combine(const bf16* a, const bf16* g, const bf16* y, bf16* out, int n, cudaStream_t stream) {
+int launch_vec_combine(const bf16* a, const bf16* g, const bf16* y, bf16* out, int rows, int B, int Dm,
+                       cudaStream_t stream) {
   count_launch(KK_MISC);
-  vec_combine_kernel<<<(n + 255) / 256, 256, 0, stream>>>(a, g, y, out, n);
+  vec_combine_kernel<<<(rows * Dm + 255) / 256, 256, 0, stream>>>(a, g, y, out, rows, B, Dm);
+  FB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Per-step scalars of the denoising loop, passed BY VALUE in the kernel parameters (no pageable/pinned staging buffer,
+// no synchronisation, capturable): t_all[s*B + b] = t_curr(s), g_all[s*B + b] = guidance, dt_tab[s][c] = bf16(t_prev - t_curr)
+// (Sampler::sample, pipelines/sampling.rs:37-44; guidance = Tensor::full, pipelines/flux/mod.rs:300-304).
+__global__ void step_scalars_kernel(const StepScalars v, int s0, int n, int B, int C, float guidance,
+                                    float* __restrict__ t_all, float* __restrict__ g_all, bf16* __restrict__ dt_tab) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * C) return;
+  const int s = i / C, c = i - s * C;
+  dt_tab[static_cast<long long>(s0 + s) * C + c] = __float2bfloat16_rn(v.dt[s]);
+  if (c < B) {
+    t_all[(s0 + s) * B + c] = v.t[s];
+    g_all[(s0 + s) * B + c] = guidance;
+  }
+}
+int launch_step_scalars(const StepScalars& v, int s0, int n, int B, int C, float guidance, float* t_all, float* g_all,
+                        bf16* dt_tab, cudaStream_t stream) {
+  FB_REQUIRE(n >= 1 && n <= StepScalars::N && B <= C, "step_scalars: bad chunk");
+  count_launch(KK_MISC);
+  step_scalars_kernel<<<(n * C + 255) / 256, 256, 0, stream>>>(v, s0, n, B, C, guidance, t_all, g_all, dt_tab);
+  FB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// end of a denoising step: advance the device-side step counter the step graph's kernels index their per-step data with
+__global__ void step_advance_kernel(int* step) { *step += 1; }
+int launch_step_advance(int* step, cudaStream_t stream) {
+  count_launch(KK_MISC);
+  step_advance_kernel<<<1, 1, 0, stream>>>(step);
+  FB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// dst[b][0 .. n16) = src[b][0 .. n16) in 16-byte units with independent batch strides (txt/img -> joint stream "cat",
+// latent staging).  A kernel instead of cudaMemcpyAsync so that the step graph consists of kernel nodes only.
+__global__ void copy_rows_kernel(uint4* __restrict__ dst, long long dst_bstride16, const uint4* __restrict__ src,
+                                 long long src_bstride16, long long n16) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= n16) return;
+  dst[blockIdx.y * dst_bstride16 + i] = src[blockIdx.y * src_bstride16 + i];
+}
+int launch_copy_rows(void* dst, long long dst_bstride_bytes, const void* src, long long src_bstride_bytes,
+                     long long bytes_per_batch, int batch, cudaStream_t stream) {
+  FB_REQUIRE(bytes_per_batch % 16 == 0 && dst_bstride_bytes % 16 == 0 && src_bstride_bytes % 16 == 0 &&
+                 (reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0,
+             "copy_rows: 16-byte granularity");
+  const long long n16 = bytes_per_batch / 16;
+  count_launch(KK_MISC);
+  copy_rows_kernel<<<dim3(static_cast<unsigned>((n16 + 255) / 256), batch), 256, 0, stream>>>(
+      static_cast<uint4*>(dst), dst_bstride_bytes / 16, static_cast<const uint4*>(src), src_bstride_bytes / 16, n16);
   FB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

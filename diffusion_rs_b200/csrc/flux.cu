@@ -122,11 +122,22 @@ struct SingleBlock {
 };
 
 struct Workspace {
+  int* step;             // device-side step counter of the denoising loop (indexes every per-step table)
+  float *t_all, *g_all;  // [steps*B] timestep / guidance value of each (step, batch element) row
+  bf16* dt_tab;          // [steps][in_channels] bf16(t_prev - t_curr), the "gate" of the fused Euler epilogue
   uint2* pe2;
   bf16 *pe_cos, *pe_sin, *temb, *gemb, *e1, *e2, *e3, *e4, *vec, *svec, *mod_all;
-  bf16 *img, *txt, *x, *xm, *qkv, *Q, *K, *V, *attn_img, *attn_txt, *big, *pred, *txt_cache;
-  float* tvals;
+  bf16 *lat, *img, *txt, *x, *xm, *qkv, *Q, *K, *V, *attn_img, *attn_txt, *big, *txt_cache;
   size_t total = 0;
+};
+
+// One captured denoising step (CUDA graph) for a given workspace / geometry / kernel-flag combination.
+struct StepGraph {
+  void* ws_base = nullptr;
+  int B = 0, l_img = 0, l_txt = 0;
+  unsigned flags_sig = 0;
+  cudaGraphExec_t exec = nullptr;
+  unsigned long long launches[KK_COUNT] = {0};  // kernels per replay, by kind (launch accounting)
 };
 
 }  // namespace fb
@@ -141,14 +152,20 @@ struct fluxb200_model {
   std::vector<DoubleBlock> dbl;
   std::vector<SingleBlock> sgl;
   std::vector<void*> owned;  // every cudaMalloc the model owns besides `raw`
-  // modulation GEMV job table (dense models): all 2*19 + 38 + 1 projections of silu(vec_) in one launch
-  GemvJob* mod_jobs_dev = nullptr;
-  int mod_njobs = 0, mod_total_rows = 0;
-  std::vector<long long> mod_off;  // offset (elements, per batch row) of each job's output inside mod_all
+  // modulation projections: all 2*19 + 38 + 1 Linears of silu(vec_); their outputs for EVERY step of an image are
+  // computed before the loop as M = steps*B row GEMMs into mod_all [steps*B][mod_row_elems]
+  std::vector<const FusedLinear*> mods;
+  std::vector<long long> mod_off;  // offset (elements, per row) of each projection's output inside a mod_all row
   long long mod_row_elems = 0;
-  bf16* wscratch = nullptr;  // dequantised-weight staging (quantised models only)
+  bf16* wscratch[2] = {nullptr, nullptr};  // dequantised-weight staging, double-buffered (quantised models only)
+  int wscratch_cur = 0;
   size_t wscratch_elems = 0;
   bool any_quant = false;
+  // step graph (denoise): captured on a private stream, replayed on the caller's
+  cudaStream_t cap_stream = nullptr;
+  std::vector<StepGraph> graphs;
+  int last_used_graph = 0;
+  std::string graph_note;
   // last forward's geometry, for the parity taps
   int last_B = 0, last_limg = 0, last_ltxt = 0;
   Workspace last_ws{};
@@ -323,43 +340,60 @@ static void drop_raw_dense(fluxb200_model* m, const FusedLinear& fl) {
   }
 }
 
-// Weight operand for the GEMM: dense pointer, or expand the quantised members into the staging buffer.
-static int weight_operand(fluxb200_model* m, const FusedLinear& fl, const bf16** w, cudaStream_t st,
-                          bool for_gemm = true) {
+// Can this quantised linear run on the fused-dequant GEMM producer?  Mirrors launch_gemm's own checks so that a layer
+// that does not qualify (x_embedder with K = 64, a blocksize that does not divide K, ...) falls back to the staging
+// expansion instead of failing at step time.
+static bool fused_dequant_ok(const FusedLinear& fl) {
+  if (fl.N % 128 != 0 || fl.K % 64 != 0 || fl.members.empty() || fl.members.size() > 4) return false;
+  for (const Member& mb : fl.members) {
+    if (mb.row_off % 128 != 0) return false;
+    if (mb.q == Q_NF4 || mb.q == Q_FP4) {
+      if (mb.blocksize % 64 != 0 || fl.K % mb.blocksize != 0) return false;
+      const int nabs = fl.K / mb.blocksize;
+      if (nabs < 4 || nabs % 4 != 0) return false;
+      if ((reinterpret_cast<uintptr_t>(mb.absmax) & 15) != 0) return false;
+    } else if (mb.q == Q_Q4K) {
+      if (fl.K % 256 != 0) return false;
+    } else if (mb.q == Q_INT8) {
+      if (mb.scb == nullptr) return false;
+    }
+    if ((reinterpret_cast<uintptr_t>(mb.packed) & 15) != 0) return false;
+  }
+  return true;
+}
+
+// Weight operand for the GEMM: dense pointer, or expand the quantised members into a staging buffer (ONE launch for
+// all members of the fused linear).  The two staging buffers alternate so that the expansion of the next layer never
+// has to wait for the GEMM that is still reading the previous one.
+static int weight_operand(fluxb200_model* m, const FusedLinear& fl, const bf16** w, cudaStream_t st) {
   if (!fl.quant) {
     *w = fl.w;
     return 0;
   }
-  if (for_gemm && get_flag("fused_dequant") && fl.N % 128 == 0 && fl.K % 64 == 0) {
+  if (get_flag("fused_dequant") && fused_dequant_ok(fl)) {
     *w = nullptr;  // gemm_for() switches to the fused-dequant producer
     return 0;
   }
+  bf16* stage = m->wscratch[m->wscratch_cur];
+  m->wscratch_cur ^= 1;
+  DequantBatch batch;
+  batch.count = 0;
   for (auto& mb : fl.members) {
-    bf16* dst = m->wscratch + static_cast<size_t>(mb.row_off) * fl.K;
-    const long long n = static_cast<long long>(mb.N) * fl.K;
-    int rc = 0;
-    switch (mb.q) {
-      case Q_NF4:
-      case Q_FP4:
-        rc = launch_dequant_bnb4(mb.packed, mb.absmax, dst, mb.blocksize, n, mb.q == Q_NF4, st);
-        break;
-      case Q_INT8:
-        rc = launch_dequant_int8(reinterpret_cast<const int8_t*>(mb.packed), mb.scb, dst, fl.K, n, st);
-        break;
-      case Q_Q4K:
-        rc = launch_dequant_q4k(mb.packed, dst, n, st);
-        break;
-      default:
-        return fail("weight_operand: bad quant type");
-    }
-    if (rc) return rc;
+    FB_REQUIRE(batch.count < DequantBatch::MAX, "weight_operand: too many fused members");
+    DequantJob& j = batch.job[batch.count++];
+    j.packed = mb.packed, j.absmax = mb.absmax, j.scb = mb.scb;
+    j.out = stage + static_cast<size_t>(mb.row_off) * fl.K;
+    j.n = static_cast<long long>(mb.N) * fl.K;
+    j.col = fl.K, j.blocksize = mb.blocksize;
+    j.kind = mb.q == Q_NF4 ? QB_NF4 : (mb.q == Q_FP4 ? QB_FP4 : (mb.q == Q_Q4K ? QB_Q4K : QB_INT8));
   }
-  *w = m->wscratch;
+  if (int rc = launch_dequant_batch(batch, st)) return rc;
+  *w = stage;
   return 0;
 }
 
-// Dense: W read by TMA.  Quantised: the GEMM's producer warps expand the packed weights on the fly (fb::QuantB),
-// unless fused de-quantisation is switched off ("fused_dequant" = 0), in which case `w` is the staging buffer.
+// Dense: W read by TMA.  Quantised: `w` is the staging buffer, or nullptr when the GEMM's producer warps expand the
+// packed weights on the fly (fb::QuantB, "fused_dequant" = 1).
 static GemmDesc gemm_for(const FusedLinear& fl, const bf16* w, const bf16* a, int M, bf16* out, int64_t ldo) {
   GemmDesc d;
   d.a = a, d.lda = fl.K, d.w = w, d.ldb = fl.K;
@@ -372,10 +406,9 @@ static GemmDesc gemm_for(const FusedLinear& fl, const bf16* w, const bf16* a, in
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-static void attach_qkrope(GemmDesc& g, const Workspace& w, const bf16* nq, const bf16* nk, int H, int L, int l_off,
-                          int rows_per_batch, float eps);
-
-static Workspace carve(const fluxb200_model* m, void* base, int B, int l_img, int l_txt) {
+// `steps` = number of denoising steps whose per-step tables (t, dt, vec_, every modulation vector) live in the
+// workspace: 1 for a single Flux::forward, n_timesteps - 1 for the denoising loop.
+static Workspace carve(const fluxb200_model* m, void* base, int B, int l_img, int l_txt, int steps) {
   Workspace w{};
   uint8_t* p = static_cast<uint8_t*>(base);
   size_t off = 0;
@@ -386,19 +419,25 @@ static Workspace carve(const fluxb200_model* m, void* base, int B, int l_img, in
   };
   const size_t L = static_cast<size_t>(l_img) + l_txt;
   const size_t Mi = static_cast<size_t>(B) * l_img, Mt = static_cast<size_t>(B) * l_txt, Mx = B * L;
-  w.tvals = static_cast<float*>(take(MAX_STEPS * 16 * 4));  // per step: t[8] | guidance[8]
+  const size_t rows = static_cast<size_t>(steps) * B;
+  const size_t C = static_cast<size_t>(m->cfg.in_channels);
+  w.step = static_cast<int*>(take(64));
+  w.t_all = static_cast<float*>(take(rows * 4));
+  w.g_all = static_cast<float*>(take(rows * 4));
+  w.dt_tab = static_cast<bf16*>(take(static_cast<size_t>(steps) * C * 2));
   w.pe_cos = static_cast<bf16*>(take(Mx * 64 * 2));
   w.pe_sin = static_cast<bf16*>(take(Mx * 64 * 2));
   w.pe2 = static_cast<uint2*>(take(Mx * 64 * 8));
-  w.temb = static_cast<bf16*>(take(static_cast<size_t>(B) * 256 * 2));
+  w.temb = static_cast<bf16*>(take(rows * 256 * 2));
   w.gemb = static_cast<bf16*>(take(static_cast<size_t>(B) * 256 * 2));
-  w.e1 = static_cast<bf16*>(take(static_cast<size_t>(B) * D * 2));
-  w.e2 = static_cast<bf16*>(take(static_cast<size_t>(B) * D * 2));
+  w.e1 = static_cast<bf16*>(take(rows * D * 2));
+  w.e2 = static_cast<bf16*>(take(rows * D * 2));
   w.e3 = static_cast<bf16*>(take(static_cast<size_t>(B) * D * 2));
   w.e4 = static_cast<bf16*>(take(static_cast<size_t>(B) * D * 2));
-  w.vec = static_cast<bf16*>(take(static_cast<size_t>(B) * D * 2));
-  w.svec = static_cast<bf16*>(take(static_cast<size_t>(B) * D * 2));
-  w.mod_all = static_cast<bf16*>(take(static_cast<size_t>(B) * m->mod_row_elems * 2));
+  w.vec = static_cast<bf16*>(take(rows * D * 2));
+  w.svec = static_cast<bf16*>(take(rows * D * 2));
+  w.mod_all = static_cast<bf16*>(take(rows * m->mod_row_elems * 2));
+  w.lat = static_cast<bf16*>(take(Mi * C * 2));
   w.img = static_cast<bf16*>(take(Mi * D * 2));
   w.txt = static_cast<bf16*>(take(Mt * D * 2));
   w.x = static_cast<bf16*>(take(Mx * D * 2));
@@ -410,7 +449,6 @@ static Workspace carve(const fluxb200_model* m, void* base, int B, int l_img, in
   w.attn_img = static_cast<bf16*>(take(Mi * D * 2));
   w.attn_txt = static_cast<bf16*>(take(Mt * D * 2));
   w.big = static_cast<bf16*>(take(Mx * (D + MLP_D) * 2));  // single: [attn | gelu(mlp)]; double: MLP hidden
-  w.pred = static_cast<bf16*>(take(Mi * 64 * 2));
   w.txt_cache = static_cast<bf16*>(take(Mt * D * 2));
   w.total = off;
   return w;
@@ -425,13 +463,18 @@ static void attach_qkrope(GemmDesc& g, const Workspace& w, const bf16* nq, const
   g.rows_per_batch = rows_per_batch;
 }
 
-// rank-2 Linear on [B, K] (MlpEmbedder / modulation): matmul -> bf16, + bias -> bf16.  `job` indexes the static
-// job table built at finalize; `row_base` is that job's row_begin (0 for the embedder jobs).
-static int small_linear(fluxb200_model* m, const FusedLinear& fl, int job, int row_base, const bf16* x, bf16* out_base,
-                        int B, cudaStream_t st) {
+// rank-2 Linear on [rows, K] (MlpEmbedder / Modulation): matmul -> bf16, then a separate bf16 broadcast_add
+// (unquantized/mod.rs:67; bnb the same, bitsandbytes/mod.rs:301-312); GGUF adds the bias to the f32 result.
+static int rank2_bias_mode(const FusedLinear& fl) {
+  return (fl.quant && !fl.members.empty() && fl.members[0].q == Q_Q4K) ? BIAS_FUSED : BIAS_AFTER_ROUND;
+}
+static int linear_rank2(fluxb200_model* m, const FusedLinear& fl, const bf16* x, int rows, bf16* out, int64_t ldo,
+                        cudaStream_t st) {
   const bf16* w = nullptr;
-  if (int rc = weight_operand(m, fl, &w, st, /*for_gemm=*/false)) return rc;  // quantised: expands into the staging buffer
-  return launch_gemv_jobs(m->mod_jobs_dev + job, 1, row_base, fl.N, x, fl.K, B, fl.K, out_base, st);
+  if (int rc = weight_operand(m, fl, &w, st)) return rc;
+  GemmDesc d = gemm_for(fl, w, x, rows, out, ldo);
+  d.bias_mode = rank2_bias_mode(fl);
+  return launch_gemm(&d, 1, st);
 }
 
 }  // namespace fb
@@ -456,8 +499,17 @@ int fluxb200_model_create(const fluxb200_flux_config* cfg, fluxb200_model** out)
   FB_CHECK_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
   FB_REQUIRE(major == 10, "fluxb200 needs an sm_100a (Blackwell B200) device; there is no fallback path");
   if (int rc = upload_rope_constants()) return rc;
+  // per-device kernel attributes (opt-in shared memory) are set here, not lazily inside a launch: the first launch of
+  // a denoising step may happen under stream capture
+  if (int rc = gemm_init_device()) return rc;
+  if (int rc = attention_init_device()) return rc;
   auto* m = new fluxb200_model();
   m->cfg = *cfg;
+  cudaError_t e = cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    delete m;
+    return fail(std::string("model_create: cudaStreamCreate failed: ") + cudaGetErrorString(e));
+  }
   *out = m;
   return 0;
 }
@@ -466,8 +518,11 @@ void fluxb200_model_destroy(fluxb200_model* m) {
   if (!m) return;
   for (auto& kv : m->raw) cudaFree(kv.second.dev);
   for (void* p : m->owned) cudaFree(p);
-  if (m->mod_jobs_dev) cudaFree(m->mod_jobs_dev);
-  if (m->wscratch) cudaFree(m->wscratch);
+  for (auto& g : m->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  if (m->cap_stream) cudaStreamDestroy(m->cap_stream);
+  for (int i = 0; i < 2; ++i)
+    if (m->wscratch[i]) cudaFree(m->wscratch[i]);
   delete m;
 }
 
@@ -506,6 +561,9 @@ int fluxb200_model_finalize(fluxb200_model* m, fluxb200_stream_t stream) {
   FB_REQUIRE(m, "finalize: null model");
   FB_REQUIRE(!m->finalized, "finalize called twice");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // build_linear reads quant-state tensors back with blocking copies: load_weight's async copies (possibly on a
+  // non-blocking stream) must have landed first
+  FB_CHECK_CUDA(cudaStreamSynchronize(st));
   const auto& c = m->cfg;
   std::vector<FusedLinear*> all;
   auto mk = [&](FusedLinear& fl, std::vector<std::string> names, int K, std::vector<int> Ns) -> int {
@@ -568,49 +626,23 @@ int fluxb200_model_finalize(fluxb200_model* m, fluxb200_stream_t stream) {
   FB_CHECK_CUDA(cudaStreamSynchronize(st));
   for (FusedLinear* fl : all) drop_raw_dense(m, *fl);
 
-  // modulation outputs: one row of `mod_row_elems` bf16 per batch element, job order = double (img, txt) ..., single, final
-  std::vector<const FusedLinear*> mods;
+  // modulation outputs: one row of `mod_row_elems` bf16 per (step, batch element); order = double (img, txt) ..., single, final
+  m->mods.clear();
   for (auto& b : m->dbl) {
-    mods.push_back(&b.img_mod);
-    mods.push_back(&b.txt_mod);
+    m->mods.push_back(&b.img_mod);
+    m->mods.push_back(&b.txt_mod);
   }
-  for (auto& b : m->sgl) mods.push_back(&b.mod);
-  mods.push_back(&m->final_mod);
+  for (auto& b : m->sgl) m->mods.push_back(&b.mod);
+  m->mods.push_back(&m->final_mod);
   m->mod_off.clear();
   long long off = 0;
-  for (auto* fl : mods) {
+  for (auto* fl : m->mods) {
     m->mod_off.push_back(off);
     off += fl->N;
   }
   m->mod_row_elems = off;
-  m->mod_njobs = static_cast<int>(mods.size());
-  m->mod_total_rows = static_cast<int>(off);
   if (m->any_quant) {
-    FB_CHECK_CUDA(cudaMalloc(&m->wscratch, m->wscratch_elems * 2));
-  }
-  // static GEMV job table: [modulation jobs ..., time1, time2, guid1, guid2, vecin1, vecin2]
-  {
-    std::vector<GemvJob> jobs;
-    int row = 0;
-    for (size_t i = 0; i < mods.size(); ++i) {
-      GemvJob j;
-      j.w = mods[i]->quant ? m->wscratch : mods[i]->w;
-      j.bias = mods[i]->bias, j.out_off = m->mod_off[i], j.out_ld = m->mod_row_elems;
-      j.N = mods[i]->N, j.row_begin = row;
-      j.fused_bias = (mods[i]->quant && mods[i]->members[0].q == Q_Q4K) ? 1 : 0, j.pad_ = 0;
-      row += mods[i]->N;
-      jobs.push_back(j);
-    }
-    const FusedLinear* emb[6] = {&m->time1, &m->time2, &m->guid1, &m->guid2, &m->vecin1, &m->vecin2};
-    for (int e = 0; e < 6; ++e) {
-      GemvJob j;
-      j.w = emb[e]->quant ? m->wscratch : emb[e]->w;
-      j.bias = emb[e]->bias, j.out_off = 0, j.out_ld = D, j.N = emb[e]->N, j.row_begin = 0;
-      j.fused_bias = (emb[e]->quant && !emb[e]->members.empty() && emb[e]->members[0].q == Q_Q4K) ? 1 : 0, j.pad_ = 0;
-      jobs.push_back(j);
-    }
-    FB_CHECK_CUDA(cudaMalloc(&m->mod_jobs_dev, sizeof(GemvJob) * jobs.size()));
-    FB_CHECK_CUDA(cudaMemcpy(m->mod_jobs_dev, jobs.data(), sizeof(GemvJob) * jobs.size(), cudaMemcpyHostToDevice));
+    for (int i = 0; i < 2; ++i) FB_CHECK_CUDA(cudaMalloc(&m->wscratch[i], m->wscratch_elems * 2));
   }
   m->finalized = true;
   return 0;
@@ -621,7 +653,16 @@ int fluxb200_model_workspace_size(const fluxb200_model* m, int32_t batch, int32_
                                   uint64_t* bytes) {
   FB_REQUIRE(m && bytes && m->finalized, "workspace_size: model not finalized");
   FB_REQUIRE(batch >= 1 && batch <= 8 && l_img > 0 && l_txt > 0, "workspace_size: bad geometry (batch 1..8)");
-  *bytes = carve(m, nullptr, batch, l_img, l_txt).total + 1024;
+  *bytes = carve(m, nullptr, batch, l_img, l_txt, 1).total + 1024;
+  return 0;
+}
+
+int fluxb200_model_denoise_workspace_size(const fluxb200_model* m, int32_t batch, int32_t l_img, int32_t l_txt,
+                                          int32_t n_timesteps, uint64_t* bytes) {
+  FB_REQUIRE(m && bytes && m->finalized, "denoise_workspace_size: model not finalized");
+  FB_REQUIRE(batch >= 1 && batch <= 8 && l_img > 0 && l_txt > 0, "denoise_workspace_size: bad geometry (batch 1..8)");
+  FB_REQUIRE(n_timesteps >= 2 && n_timesteps <= MAX_STEPS, "denoise_workspace_size: 2..1024 timesteps");
+  *bytes = carve(m, nullptr, batch, l_img, l_txt, n_timesteps - 1).total + 1024;
   return 0;
 }
 
@@ -630,39 +671,91 @@ int fluxb200_model_workspace_size(const fluxb200_model* m, int32_t batch, int32_
 namespace fb {
 
 struct StepIO {
-  const bf16* img_in;   // [B, l_img, 64]
   const bf16* img_ids;  // [B, l_img, 3]
   const bf16* txt_in;   // [B, l_txt, joint]
   const bf16* txt_ids;  // [B, l_txt, 3]
   const bf16* y;        // [B, pooled]
-  bf16* out;            // [B, l_img, 64]
 };
 
-// Step-invariant part: RoPE table (model.rs:807-810) and txt_in (model.rs:811)
+#define TRY(x)          \
+  do {                  \
+    int _rc = (x);      \
+    if (_rc) return _rc; \
+  } while (0)
+
+// Step-invariant part 1: RoPE table (model.rs:807-810)
 static int prepare_invariants(fluxb200_model* m, const Workspace& w, const StepIO& io, int B, int l_img, int l_txt,
                               cudaStream_t st) {
   const int L = l_img + l_txt;
-  {
-    const int n1 = B * l_txt * 64, n2 = B * l_img * 64;
-    count_launch(KK_MISC, 2);
-    pe_table_kernel<<<(n1 + 255) / 256, 256, 0, st>>>(io.txt_ids, l_txt, B, L, 0, w.pe_cos, w.pe_sin, w.pe2);
-    pe_table_kernel<<<(n2 + 255) / 256, 256, 0, st>>>(io.img_ids, l_img, B, L, l_txt, w.pe_cos, w.pe_sin, w.pe2);
-    FB_CHECK_CUDA(cudaGetLastError());
+  const int n1 = B * l_txt * 64, n2 = B * l_img * 64;
+  count_launch(KK_MISC, 2);
+  pe_table_kernel<<<(n1 + 255) / 256, 256, 0, st>>>(io.txt_ids, l_txt, B, L, 0, w.pe_cos, w.pe_sin, w.pe2);
+  pe_table_kernel<<<(n2 + 255) / 256, 256, 0, st>>>(io.img_ids, l_img, B, L, l_txt, w.pe_cos, w.pe_sin, w.pe2);
+  FB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Step-invariant part 2: txt = txt_in(txt) (model.rs:811) -> w.txt_cache; the first double block reads it from there.
+static int project_txt(fluxb200_model* m, const Workspace& w, const StepIO& io, int B, int l_txt, cudaStream_t st) {
+  const bf16* wt = nullptr;
+  TRY(weight_operand(m, m->txt_in, &wt, st));
+  GemmDesc d = gemm_for(m->txt_in, wt, io.txt_in, B * l_txt, w.txt_cache, D);
+  return launch_gemm(&d, 1, st);
+}
+
+// vec_ (model.rs:813-820) and EVERY AdaLN modulation projection (model.rs:244-299, 694-698) for `rows` = steps*B
+// (step, batch element) pairs at once.  vec_ depends only on (t, guidance, y) and all timesteps of an image are known
+// before the loop, so the 6.5 GB of modulation weights are streamed ONCE per image (M = steps*B rows on the tcgen05
+// GEMM) instead of once per step; every row keeps the reference's rounding points (the Linears are row-independent).
+//   t_all [rows] f32, g_all [>= B] f32 or nullptr (guidance does not depend on the step), y [B, pooled]
+static int compute_modulations(fluxb200_model* m, const Workspace& w, const float* t_all, const float* g_all,
+                               const bf16* y, int rows, int B, cudaStream_t st) {
+  const auto& c = m->cfg;
+  TRY(launch_timestep_embedding(t_all, w.temb, rows, 256, st));
+  TRY(linear_rank2(m, m->time1, w.temb, rows, w.e1, D, st));
+  TRY(launch_silu(w.e1, w.e1, static_cast<long long>(rows) * D, st));
+  TRY(linear_rank2(m, m->time2, w.e1, rows, w.e2, D, st));
+  const bf16* gvec = nullptr;
+  if (c.guidance_embeds && g_all) {
+    TRY(launch_timestep_embedding(g_all, w.gemb, B, 256, st));
+    TRY(linear_rank2(m, m->guid1, w.gemb, B, w.e1, D, st));
+    TRY(launch_silu(w.e1, w.e1, static_cast<long long>(B) * D, st));
+    TRY(linear_rank2(m, m->guid2, w.e1, B, w.e3, D, st));
+    gvec = w.e3;
+  }
+  TRY(linear_rank2(m, m->vecin1, y, B, w.e1, D, st));
+  TRY(launch_silu(w.e1, w.e1, static_cast<long long>(B) * D, st));
+  TRY(linear_rank2(m, m->vecin2, w.e1, B, w.e4, D, st));
+  TRY(launch_vec_combine(w.e2, gvec, w.e4, w.vec, rows, B, D, st));
+  TRY(launch_silu(w.vec, w.svec, static_cast<long long>(rows) * D, st));
+  // dense projections share launches (grouped GEMM, 4 problems each); quantised ones go one at a time through the staging buffer
+  const size_t n = m->mods.size();
+  for (size_t i = 0; i < n;) {
+    GemmDesc g[4];
+    int cnt = 0;
+    while (i < n && cnt < 4) {
+      const FusedLinear& fl = *m->mods[i];
+      if (fl.quant && cnt > 0) break;
+      const bf16* wp = nullptr;
+      TRY(weight_operand(m, fl, &wp, st));
+      g[cnt] = gemm_for(fl, wp, w.svec, rows, w.mod_all + m->mod_off[i], m->mod_row_elems);
+      g[cnt].bias_mode = rank2_bias_mode(fl);
+      ++cnt, ++i;
+      if (fl.quant) break;
+    }
+    TRY(launch_gemm(g, cnt, st));
   }
   return 0;
 }
 
-// txt = txt_in(txt) — written into w.txt (double-block stream). Step-invariant but part of Flux::forward.
-static int project_txt(fluxb200_model* m, const Workspace& w, const StepIO& io, int B, int l_txt, cudaStream_t st) {
-  const bf16* wt = nullptr;
-  if (int rc = weight_operand(m, m->txt_in, &wt, st)) return rc;
-  GemmDesc d = gemm_for(m->txt_in, wt, io.txt_in, B * l_txt, w.txt, D);
-  return launch_gemm(&d, 1, st);
-}
-
-// One Flux::forward given prepared pe table. If `txt_cached` is non-null it holds txt_in(txt) already.
-static int forward_core(fluxb200_model* m, const Workspace& w, const StepIO& io, const float* t_dev,
-                        const float* g_dev, int B, int l_img, int l_txt, const bf16* txt_cached, cudaStream_t st) {
+// One Flux::forward (model.rs:790-833) given the hoisted pieces: RoPE table, txt_in(txt) in w.txt_cache and the
+// modulation vectors in w.mod_all.
+//   step_ptr == nullptr : single forward; modulation row block 0; prediction written to `pred_out`
+//   step_ptr != nullptr : denoising step; modulation row block *step_ptr; the Euler update
+//                         img += bf16(pred * dt) (pipelines/sampling.rs:43) is the final projection's epilogue, in place
+//                         on `lat` (out = res + gate * val with gate = dt_tab[step], two roundings)
+static int step_core(fluxb200_model* m, const Workspace& w, const bf16* img_in, bf16* pred_out, bf16* lat,
+                     const int* step_ptr, int B, int l_img, int l_txt, cudaStream_t st) {
   const auto& c = m->cfg;
   const int L = l_img + l_txt;
   const int Mi = B * l_img, Mt = B * l_txt, Mx = B * L;
@@ -671,60 +764,27 @@ static int forward_core(fluxb200_model* m, const Workspace& w, const StepIO& io,
   const float scale = 1.0f / sqrtf(static_cast<float>(HEAD_DIM));
   const long long PE_BS = static_cast<long long>(L) * 64;
   const bool fuse_qk = get_flag("qkrope_fusion") != 0;
-  const int JE = m->mod_njobs;  // embedder jobs follow the modulation jobs in the static table
-  int rc = 0;
-#define TRY(x)          \
-  do {                  \
-    rc = (x);           \
-    if (rc) return rc;  \
-  } while (0)
+  const long long mstride = m->mod_row_elems;                   // batch stride inside one step's block of rows
+  const long long sstride = static_cast<long long>(B) * mstride;  // step stride
+  auto modp = [&](int job, int chunk) { return w.mod_all + m->mod_off[job] + static_cast<long long>(chunk) * D; };
+  auto ln_mod = [&](const bf16* x, int in_bstride_rows, int in_row_off, int rows_per_batch, int job, int shift_chunk,
+                    int scale_chunk, bf16* out) {
+    return launch_ln_modulate(x, in_bstride_rows, in_row_off, rows_per_batch, B, modp(job, shift_chunk),
+                              modp(job, scale_chunk), mstride, out, D, eps, st, step_ptr, sstride);
+  };
+  auto gated = [&](GemmDesc& g, int job, int gate_chunk, int rows_per_batch, const bf16* res) {
+    g.gate = modp(job, gate_chunk), g.gate_bstride = mstride, g.rows_per_batch = rows_per_batch, g.res = res;
+    g.step_ptr = step_ptr, g.gate_step_stride = sstride;
+  };
 
-  // ---- txt_in / img_in (model.rs:811-812) ----
-  if (txt_cached) {
-    FB_CHECK_CUDA(cudaMemcpyAsync(w.txt, txt_cached, static_cast<size_t>(Mt) * D * 2, cudaMemcpyDeviceToDevice, st));
-  } else {
-    TRY(project_txt(m, w, io, B, l_txt, st));
-  }
+  // ---- img_in (model.rs:812); txt_in(txt) was hoisted ----
   {
     const bf16* wi = nullptr;
     TRY(weight_operand(m, m->img_in, &wi, st));
-    GemmDesc d = gemm_for(m->img_in, wi, io.img_in, Mi, w.img, D);
+    GemmDesc d = gemm_for(m->img_in, wi, img_in, Mi, w.img, D);
     TRY(launch_gemm(&d, 1, st));
   }
-  // ---- vec_ (model.rs:813-820) ----
-  TRY(launch_timestep_embedding(t_dev, w.temb, B, 256, st));
-  TRY(small_linear(m, m->time1, JE + 0, 0, w.temb, w.e1, B, st));
-  TRY(launch_silu(w.e1, w.e1, static_cast<long long>(B) * D, st));
-  TRY(small_linear(m, m->time2, JE + 1, 0, w.e1, w.e2, B, st));
-  const bf16* gvec = nullptr;
-  if (c.guidance_embeds && g_dev) {
-    TRY(launch_timestep_embedding(g_dev, w.gemb, B, 256, st));
-    TRY(small_linear(m, m->guid1, JE + 2, 0, w.gemb, w.e1, B, st));
-    TRY(launch_silu(w.e1, w.e1, static_cast<long long>(B) * D, st));
-    TRY(small_linear(m, m->guid2, JE + 3, 0, w.e1, w.e3, B, st));
-    gvec = w.e3;
-  }
-  TRY(small_linear(m, m->vecin1, JE + 4, 0, io.y, w.e1, B, st));
-  TRY(launch_silu(w.e1, w.e1, static_cast<long long>(B) * D, st));
-  TRY(small_linear(m, m->vecin2, JE + 5, 0, w.e1, w.e4, B, st));
-  TRY(launch_vec_combine(w.e2, gvec, w.e4, w.vec, B * D, st));
-  // ---- every modulation projection of silu(vec_) (model.rs:244-299, 694-698) ----
-  TRY(launch_silu(w.vec, w.svec, static_cast<long long>(B) * D, st));
-  if (!m->any_quant) {
-    TRY(launch_gemv_jobs(m->mod_jobs_dev, m->mod_njobs, 0, m->mod_total_rows, w.svec, D, B, D, w.mod_all, st));
-  } else {
-    std::vector<const FusedLinear*> mods;
-    for (auto& b : m->dbl) {
-      mods.push_back(&b.img_mod);
-      mods.push_back(&b.txt_mod);
-    }
-    for (auto& b : m->sgl) mods.push_back(&b.mod);
-    mods.push_back(&m->final_mod);
-    for (size_t i = 0; i < mods.size(); ++i)
-      TRY(small_linear(m, *mods[i], static_cast<int>(i), static_cast<int>(m->mod_off[i]), w.svec, w.mod_all, B, st));
-  }
-  const long long mstride = m->mod_row_elems;
-  auto modp = [&](int job, int chunk) { return w.mod_all + m->mod_off[job] + static_cast<long long>(chunk) * D; };
+  const bf16* txt_cur = w.txt_cache;  // the txt stream is read from the hoisted projection until its first update
 
   // ---- double-stream blocks (model.rs:523-565) ----
   for (int i = 0; i < c.num_layers; ++i) {
@@ -734,29 +794,35 @@ static int forward_core(fluxb200_model* m, const Workspace& w, const StepIO& io,
     bf16* xm_txt = w.xm + static_cast<size_t>(Mi) * D;
     bf16* qkv_img = w.qkv;
     bf16* qkv_txt = w.qkv + static_cast<size_t>(Mi) * 3 * D;
-    TRY(launch_ln_modulate(w.img, l_img, 0, l_img, B, modp(ji, 0), modp(ji, 1), mstride, xm_img, D, eps, st));
-    TRY(launch_ln_modulate(w.txt, l_txt, 0, l_txt, B, modp(jt, 0), modp(jt, 1), mstride, xm_txt, D, eps, st));
-    {
-      const bf16 *wi = nullptr, *wt = nullptr;
-      GemmDesc g[2];
-      if (!b.img_qkv.quant) {
-        g[0] = gemm_for(b.img_qkv, b.img_qkv.w, xm_img, Mi, qkv_img, 3 * D);
-        g[1] = gemm_for(b.txt_qkv, b.txt_qkv.w, xm_txt, Mt, qkv_txt, 3 * D);
-        if (fuse_qk) {
-          attach_qkrope(g[0], w, b.img_nq, b.img_nk, H, L, l_txt, l_img, eps);
-          attach_qkrope(g[1], w, b.txt_nq, b.txt_nk, H, L, 0, l_txt, eps);
-        }
-        TRY(launch_gemm(g, 2, st));
-      } else {  // one staging buffer: expand and run the two streams back to back
-        TRY(weight_operand(m, b.img_qkv, &wi, st));
-        g[0] = gemm_for(b.img_qkv, wi, xm_img, Mi, qkv_img, 3 * D);
-        if (fuse_qk) attach_qkrope(g[0], w, b.img_nq, b.img_nk, H, L, l_txt, l_img, eps);
-        TRY(launch_gemm(g, 1, st));
-        TRY(weight_operand(m, b.txt_qkv, &wt, st));
-        g[1] = gemm_for(b.txt_qkv, wt, xm_txt, Mt, qkv_txt, 3 * D);
-        if (fuse_qk) attach_qkrope(g[1], w, b.txt_nq, b.txt_nk, H, L, 0, l_txt, eps);
-        TRY(launch_gemm(g + 1, 1, st));
+    TRY(ln_mod(w.img, l_img, 0, l_img, ji, 0, 1, xm_img));
+    TRY(ln_mod(txt_cur, l_txt, 0, l_txt, jt, 0, 1, xm_txt));
+    // img and txt problems share one launch when both weights are dense; a quantised weight goes through the (reused)
+    // staging buffer, so those problems are launched one by one right after their expansion
+    auto two = [&](FusedLinear& fi, FusedLinear& ft, GemmDesc& gi, GemmDesc& gt) -> int {
+      if (!fi.quant && !ft.quant) {
+        GemmDesc g[2] = {gi, gt};
+        g[0].w = fi.w, g[1].w = ft.w;
+        return launch_gemm(g, 2, st);
       }
+      for (int s = 0; s < 2; ++s) {
+        FusedLinear& f = s == 0 ? fi : ft;
+        GemmDesc& g = s == 0 ? gi : gt;
+        const bf16* wq = nullptr;
+        if (int r = weight_operand(m, f, &wq, st)) return r;
+        g.w = wq;
+        g.qb = (f.quant && wq == nullptr) ? &f.qb : nullptr;
+        if (int r = launch_gemm(&g, 1, st)) return r;
+      }
+      return 0;
+    };
+    {
+      GemmDesc gi = gemm_for(b.img_qkv, nullptr, xm_img, Mi, qkv_img, 3 * D);
+      GemmDesc gt = gemm_for(b.txt_qkv, nullptr, xm_txt, Mt, qkv_txt, 3 * D);
+      if (fuse_qk) {
+        attach_qkrope(gi, w, b.img_nq, b.img_nk, H, L, l_txt, l_img, eps);
+        attach_qkrope(gt, w, b.txt_nq, b.txt_nk, H, L, 0, l_txt, eps);
+      }
+      TRY(two(b.img_qkv, b.txt_qkv, gi, gt));
     }
     if (!fuse_qk) {
       TRY(launch_qknorm_rope(qkv_txt, 3 * D, l_txt, B, H, L, 0, b.txt_nq, b.txt_nk, w.pe_cos, w.pe_sin, PE_BS, w.Q,
@@ -770,56 +836,45 @@ static int forward_core(fluxb200_model* m, const Workspace& w, const StepIO& io,
       a.out_a = w.attn_txt, a.ld_a = D, a.out_b = w.attn_img, a.ld_b = D, a.l_split = l_txt;
       TRY(launch_attention(a, st));
     }
-    auto two = [&](FusedLinear& fi, FusedLinear& ft, const bf16* ai, const bf16* at, bf16* oi, bf16* ot, int64_t ldo,
-                   int act, int gate_chunk, bool residual) -> int {
-      GemmDesc g[2];
-      const bf16 *wi = fi.w, *wt = ft.w;
-      for (int s = 0; s < 2; ++s) {
-        FusedLinear& f = s == 0 ? fi : ft;
-        if (f.quant) {
-          const bf16* wq = nullptr;
-          if (int r = weight_operand(m, f, &wq, st)) return r;
-          (s == 0 ? wi : wt) = wq;
-        }
-        g[s] = gemm_for(f, s == 0 ? wi : wt, s == 0 ? ai : at, s == 0 ? Mi : Mt, s == 0 ? oi : ot, ldo);
-        g[s].act0 = act;
-        if (residual) {
-          g[s].gate = modp(s == 0 ? ji : jt, gate_chunk);
-          g[s].gate_bstride = mstride;
-          g[s].rows_per_batch = s == 0 ? l_img : l_txt;
-          g[s].res = s == 0 ? oi : ot;
-        }
-        if (f.quant)
-          if (int r = launch_gemm(&g[s], 1, st)) return r;
-      }
-      if (!fi.quant) return launch_gemm(g, 2, st);
-      return 0;
-    };
-    // img/txt += gate1 * proj(attn)
-    TRY(two(b.img_proj, b.txt_proj, w.attn_img, w.attn_txt, w.img, w.txt, D, ACT_NONE, 2, true));
+    {  // img/txt += gate1 * proj(attn)
+      GemmDesc gi = gemm_for(b.img_proj, nullptr, w.attn_img, Mi, w.img, D);
+      GemmDesc gt = gemm_for(b.txt_proj, nullptr, w.attn_txt, Mt, w.txt, D);
+      gated(gi, ji, 2, l_img, w.img);
+      gated(gt, jt, 2, l_txt, txt_cur);
+      TRY(two(b.img_proj, b.txt_proj, gi, gt));
+      txt_cur = w.txt;
+    }
     // MLP: x += gate2 * lin2(gelu(lin1(modulate2(LN(x)))))
-    TRY(launch_ln_modulate(w.img, l_img, 0, l_img, B, modp(ji, 3), modp(ji, 4), mstride, xm_img, D, eps, st));
-    TRY(launch_ln_modulate(w.txt, l_txt, 0, l_txt, B, modp(jt, 3), modp(jt, 4), mstride, xm_txt, D, eps, st));
+    TRY(ln_mod(w.img, l_img, 0, l_img, ji, 3, 4, xm_img));
+    TRY(ln_mod(w.txt, l_txt, 0, l_txt, jt, 3, 4, xm_txt));
     bf16* h_img = w.big;
     bf16* h_txt = w.big + static_cast<size_t>(Mi) * MLP_D;
-    TRY(two(b.img_mlp1, b.txt_mlp1, xm_img, xm_txt, h_img, h_txt, MLP_D, ACT_GELU, 0, false));
-    TRY(two(b.img_mlp2, b.txt_mlp2, h_img, h_txt, w.img, w.txt, D, ACT_NONE, 5, true));
+    {
+      GemmDesc gi = gemm_for(b.img_mlp1, nullptr, xm_img, Mi, h_img, MLP_D);
+      GemmDesc gt = gemm_for(b.txt_mlp1, nullptr, xm_txt, Mt, h_txt, MLP_D);
+      gi.act0 = gt.act0 = ACT_GELU;
+      TRY(two(b.img_mlp1, b.txt_mlp1, gi, gt));
+    }
+    {
+      GemmDesc gi = gemm_for(b.img_mlp2, nullptr, h_img, Mi, w.img, D);
+      GemmDesc gt = gemm_for(b.txt_mlp2, nullptr, h_txt, Mt, w.txt, D);
+      gated(gi, ji, 5, l_img, w.img);
+      gated(gt, jt, 5, l_txt, w.txt);
+      TRY(two(b.img_mlp2, b.txt_mlp2, gi, gt));
+    }
   }
 
   // ---- cat(txt, img) (model.rs:827) ----
-  for (int bi = 0; bi < B; ++bi) {
-    FB_CHECK_CUDA(cudaMemcpyAsync(w.x + (static_cast<size_t>(bi) * L) * D, w.txt + static_cast<size_t>(bi) * l_txt * D,
-                                  static_cast<size_t>(l_txt) * D * 2, cudaMemcpyDeviceToDevice, st));
-    FB_CHECK_CUDA(cudaMemcpyAsync(w.x + (static_cast<size_t>(bi) * L + l_txt) * D,
-                                  w.img + static_cast<size_t>(bi) * l_img * D, static_cast<size_t>(l_img) * D * 2,
-                                  cudaMemcpyDeviceToDevice, st));
-  }
+  TRY(launch_copy_rows(w.x, static_cast<long long>(L) * D * 2, txt_cur, static_cast<long long>(l_txt) * D * 2,
+                       static_cast<long long>(l_txt) * D * 2, B, st));
+  TRY(launch_copy_rows(w.x + static_cast<size_t>(l_txt) * D, static_cast<long long>(L) * D * 2, w.img,
+                       static_cast<long long>(l_img) * D * 2, static_cast<long long>(l_img) * D * 2, B, st));
   // ---- single-stream blocks (model.rs:638-662) ----
   const int CAT = D + MLP_D;
   for (int i = 0; i < c.num_single_layers; ++i) {
     SingleBlock& b = m->sgl[i];
     const int j = 2 * c.num_layers + i;  // chunks = shift, scale, gate
-    TRY(launch_ln_modulate(w.x, L, 0, L, B, modp(j, 0), modp(j, 1), mstride, w.xm, D, eps, st));
+    TRY(ln_mod(w.x, L, 0, L, j, 0, 1, w.xm));
     {
       const bf16* w1 = nullptr;
       TRY(weight_operand(m, b.lin1, &w1, st));
@@ -841,36 +896,102 @@ static int forward_core(fluxb200_model* m, const Workspace& w, const StepIO& io,
       const bf16* w2 = nullptr;
       TRY(weight_operand(m, b.lin2, &w2, st));
       GemmDesc g = gemm_for(b.lin2, w2, w.big, Mx, w.x, D);
-      g.gate = modp(j, 2), g.gate_bstride = mstride, g.rows_per_batch = L, g.res = w.x;
+      gated(g, j, 2, L, w.x);
       TRY(launch_gemm(&g, 1, st));
     }
   }
   // ---- final layer on the img rows (model.rs:831-832, 694-705): chunks = scale, shift ----
   {
     const int jf = 2 * c.num_layers + c.num_single_layers;
-    TRY(launch_ln_modulate(w.x, L, l_txt, l_img, B, modp(jf, 1), modp(jf, 0), mstride, w.xm, D, eps, st));
+    TRY(ln_mod(w.x, L, l_txt, l_img, jf, 1, 0, w.xm));
     const bf16* wf = nullptr;
     TRY(weight_operand(m, m->final_proj, &wf, st));
-    GemmDesc g = gemm_for(m->final_proj, wf, w.xm, Mi, io.out, c.in_channels);
+    GemmDesc g = gemm_for(m->final_proj, wf, w.xm, Mi, step_ptr ? lat : pred_out, c.in_channels);
+    if (step_ptr) {  // fused Euler update
+      g.gate = w.dt_tab, g.gate_bstride = 0, g.rows_per_batch = l_img, g.res = lat;
+      g.step_ptr = step_ptr, g.gate_step_stride = c.in_channels;
+    }
     TRY(launch_gemm(&g, 1, st));
   }
-  m->last_B = B, m->last_limg = l_img, m->last_ltxt = l_txt, m->last_ws = w;
   return 0;
-#undef TRY
 }
 
-static int check_ws(fluxb200_model* m, int B, int l_img, int l_txt, void* ws, uint64_t ws_bytes, Workspace* out) {
+static int check_ws(fluxb200_model* m, int B, int l_img, int l_txt, int steps, void* ws, uint64_t ws_bytes,
+                    Workspace* out) {
   FB_REQUIRE(m && m->finalized, "model not finalized");
   FB_REQUIRE(B >= 1 && B <= 8, "batch must be in 1..8 per call");
   FB_REQUIRE(l_img > 0 && l_txt > 0, "empty sequence");
   FB_REQUIRE(ws != nullptr, "null workspace");
   uint8_t* base = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(ws), 1024));
   const size_t slack = base - static_cast<uint8_t*>(ws);
-  Workspace w = carve(m, base, B, l_img, l_txt);
+  Workspace w = carve(m, base, B, l_img, l_txt, steps);
   FB_REQUIRE(w.total + slack <= ws_bytes, "workspace too small: need " + std::to_string(w.total + 1024) + " bytes");
   *out = w;
   return 0;
 }
+
+static unsigned flags_signature() {
+  unsigned s = 0;
+  s = s * 2 + (get_flag("qkrope_fusion") & 1);
+  s = s * 2 + (get_flag("pdl") & 1);
+  s = s * 2 + (get_flag("fused_dequant") & 1);
+  s = s * 2 + (get_flag("gemm_pair") & 1);
+  s = s * 2 + (get_flag("gemm_cl4") & 1);
+  s = s * 16 + (get_flag("gemm_big") & 15);
+  s = s * 64 + (get_flag("attn_variant") & 63);
+  return s;
+}
+
+// The denoising step as a CUDA graph: captured once per (workspace, geometry, kernel flags) on the model's private
+// stream — every tensor map, launch attribute (clusters, programmatic dependent launch edges) and kernel parameter
+// block is encoded at capture time — and replayed once per step; what changes from step to step is read by the
+// kernels through the device-side step counter.  Returns nullptr (with m->graph_note set) when capture is not possible.
+static StepGraph* step_graph_for(fluxb200_model* m, const Workspace& w, void* ws_base, int B, int l_img, int l_txt) {
+  const unsigned sig = flags_signature();
+  for (auto& g : m->graphs)
+    if (g.ws_base == ws_base && g.B == B && g.l_img == l_img && g.l_txt == l_txt && g.flags_sig == sig) return &g;
+  if (m->graphs.size() >= 8) {  // bounded cache: drop the oldest capture
+    if (m->graphs.front().exec) cudaGraphExecDestroy(m->graphs.front().exec);
+    m->graphs.erase(m->graphs.begin());
+  }
+  StepGraph sg;
+  sg.ws_base = ws_base, sg.B = B, sg.l_img = l_img, sg.l_txt = l_txt, sg.flags_sig = sig;
+  unsigned long long before[KK_COUNT], after[KK_COUNT];
+  snapshot_launches(before);
+  const int scratch_cur = m->wscratch_cur;
+  cudaError_t e = cudaStreamBeginCapture(m->cap_stream, cudaStreamCaptureModeThreadLocal);
+  if (e != cudaSuccess) {
+    m->graph_note = std::string("cudaStreamBeginCapture failed: ") + cudaGetErrorString(e);
+    cudaGetLastError();
+    return nullptr;
+  }
+  int rc = step_core(m, w, w.lat, nullptr, w.lat, w.step, B, l_img, l_txt, m->cap_stream);
+  if (rc == 0) rc = launch_step_advance(w.step, m->cap_stream);
+  cudaGraph_t graph = nullptr;
+  e = cudaStreamEndCapture(m->cap_stream, &graph);
+  snapshot_launches(after);
+  for (int k = 0; k < KK_COUNT; ++k) sg.launches[k] = after[k] - before[k];
+  count_launch_bulk(sg.launches, -1);  // nothing was launched while capturing
+  m->wscratch_cur = scratch_cur;       // every replay starts from the staging buffer the capture started from
+  if (rc != 0 || e != cudaSuccess || graph == nullptr) {
+    m->graph_note = rc != 0 ? std::string("capture failed: ") + last_error()
+                            : std::string("cudaStreamEndCapture failed: ") + cudaGetErrorString(e);
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    return nullptr;
+  }
+  e = cudaGraphInstantiate(&sg.exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) {
+    m->graph_note = std::string("cudaGraphInstantiate failed: ") + cudaGetErrorString(e);
+    cudaGetLastError();
+    return nullptr;
+  }
+  m->graphs.push_back(sg);
+  return &m->graphs.back();
+}
+
+#undef TRY
 
 }  // namespace fb
 
@@ -882,13 +1003,20 @@ int fluxb200_model_forward(fluxb200_model* m, const void* img, const void* img_i
                            uint64_t workspace_bytes, fluxb200_stream_t stream) {
   FB_REQUIRE(img && img_ids && txt && txt_ids && timesteps && y && out, "forward: null tensor");
   Workspace w;
-  if (int rc = check_ws(m, batch, l_img, l_txt, workspace, workspace_bytes, &w)) return rc;
+  if (int rc = check_ws(m, batch, l_img, l_txt, 1, workspace, workspace_bytes, &w)) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  StepIO io{static_cast<const bf16*>(img), static_cast<const bf16*>(img_ids), static_cast<const bf16*>(txt),
-            static_cast<const bf16*>(txt_ids), static_cast<const bf16*>(y), static_cast<bf16*>(out)};
+  StepIO io{static_cast<const bf16*>(img_ids), static_cast<const bf16*>(txt), static_cast<const bf16*>(txt_ids),
+            static_cast<const bf16*>(y)};
   if (int rc = prepare_invariants(m, w, io, batch, l_img, l_txt, st)) return rc;
-  return forward_core(m, w, io, static_cast<const float*>(timesteps), static_cast<const float*>(guidance), batch,
-                      l_img, l_txt, nullptr, st);
+  if (int rc = project_txt(m, w, io, batch, l_txt, st)) return rc;
+  if (int rc = compute_modulations(m, w, static_cast<const float*>(timesteps), static_cast<const float*>(guidance),
+                                   io.y, batch, batch, st))
+    return rc;
+  if (int rc = step_core(m, w, static_cast<const bf16*>(img), static_cast<bf16*>(out), nullptr, nullptr, batch, l_img,
+                         l_txt, st))
+    return rc;
+  m->last_B = batch, m->last_limg = l_img, m->last_ltxt = l_txt, m->last_ws = w;
+  return 0;
 }
 
 int fluxb200_model_denoise(fluxb200_model* m, void* img, const void* img_ids, const void* txt, const void* txt_ids,
@@ -897,38 +1025,64 @@ int fluxb200_model_denoise(fluxb200_model* m, void* img, const void* img_ids, co
                            fluxb200_stream_t stream) {
   FB_REQUIRE(img && img_ids && txt && txt_ids && y && timesteps, "denoise: null tensor");
   FB_REQUIRE(n_timesteps >= 2, "denoise: need at least two timesteps");
-  Workspace w;
-  if (int rc = check_ws(m, batch, l_img, l_txt, workspace, workspace_bytes, &w)) return rc;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  StepIO io{static_cast<const bf16*>(img), static_cast<const bf16*>(img_ids), static_cast<const bf16*>(txt),
-            static_cast<const bf16*>(txt_ids), static_cast<const bf16*>(y), w.pred};
-  if (int rc = prepare_invariants(m, w, io, batch, l_img, l_txt, st)) return rc;
-  // txt_in(txt) does not depend on t: project once, keep it in the workspace and copy it into the stream buffer
-  // at the start of every step.
   FB_REQUIRE(n_timesteps <= MAX_STEPS, "denoise: at most 1024 timesteps");
-  const size_t txt_bytes = static_cast<size_t>(batch) * l_txt * D * 2;
+  const int steps = n_timesteps - 1;
+  Workspace w;
+  if (int rc = check_ws(m, batch, l_img, l_txt, steps, workspace, workspace_bytes, &w)) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  StepIO io{static_cast<const bf16*>(img_ids), static_cast<const bf16*>(txt), static_cast<const bf16*>(txt_ids),
+            static_cast<const bf16*>(y)};
+  const int C = m->cfg.in_channels;
+  const long long lat_bytes = static_cast<long long>(batch) * l_img * C * 2;
+  FB_REQUIRE((reinterpret_cast<uintptr_t>(img) & 15) == 0, "denoise: img must be 16-byte aligned");
+  // ---- per-image prologue: everything that does not depend on the evolving latent ----
+  // the latent lives in the workspace during the loop (the step graph is bound to workspace addresses only)
+  if (int rc = launch_copy_rows(w.lat, 0, img, 0, lat_bytes, 1, st)) return rc;
+  if (int rc = prepare_invariants(m, w, io, batch, l_img, l_txt, st)) return rc;
   if (int rc = project_txt(m, w, io, batch, l_txt, st)) return rc;
-  FB_CHECK_CUDA(cudaMemcpyAsync(w.txt_cache, w.txt, txt_bytes, cudaMemcpyDeviceToDevice, st));
-  // t_vec = full(1) * t_curr (f32); guidance = full(guidance_scale) (pipelines/flux/mod.rs:300-304, sampling.rs:42).
-  // All per-step scalars are uploaded once, before the loop.
-  std::vector<float> hv(static_cast<size_t>(n_timesteps) * 16, 0.f);
-  for (int s = 0; s + 1 < n_timesteps; ++s)
-    for (int b = 0; b < batch; ++b) {
-      hv[s * 16 + b] = static_cast<float>(1.0f * timesteps[s]);
-      hv[s * 16 + 8 + b] = guidance_scale;
+  // t_vec = full(1) * t_curr (f32); guidance = full(guidance_scale) (pipelines/flux/mod.rs:300-304, sampling.rs:42);
+  // dt = t_prev - t_curr.  The scalars travel as kernel parameters: no staging buffer, no synchronisation.
+  for (int s0 = 0; s0 < steps; s0 += StepScalars::N) {
+    StepScalars sv;
+    const int n = std::min(StepScalars::N, steps - s0);
+    for (int i = 0; i < n; ++i) {
+      sv.t[i] = static_cast<float>(1.0f * timesteps[s0 + i]);
+      sv.dt[i] = static_cast<float>(timesteps[s0 + i + 1] - timesteps[s0 + i]);
     }
-  FB_CHECK_CUDA(cudaMemcpyAsync(w.tvals, hv.data(), hv.size() * 4, cudaMemcpyHostToDevice, st));
-  FB_CHECK_CUDA(cudaStreamSynchronize(st));  // `hv` is pageable host memory: make sure the copy has consumed it
-  for (int s = 0; s + 1 < n_timesteps; ++s) {
-    const double t_curr = timesteps[s], t_prev = timesteps[s + 1];
-    const float* tv = w.tvals + s * 16;
-    if (int rc = forward_core(m, w, io, tv, m->cfg.guidance_embeds ? tv + 8 : nullptr, batch, l_img, l_txt,
-                              w.txt_cache, st))
-      return rc;
-    if (int rc = launch_euler(static_cast<bf16*>(img), w.pred, static_cast<float>(t_prev - t_curr),
-                              static_cast<long long>(batch) * l_img * m->cfg.in_channels, st))
-      return rc;
+    if (int rc = launch_step_scalars(sv, s0, n, batch, C, guidance_scale, w.t_all, w.g_all, w.dt_tab, st)) return rc;
   }
+  FB_CHECK_CUDA(cudaMemsetAsync(w.step, 0, 64, st));
+  if (int rc = compute_modulations(m, w, w.t_all, m->cfg.guidance_embeds ? w.g_all : nullptr, io.y, steps * batch,
+                                   batch, st))
+    return rc;
+  // ---- the loop: one graph replay per step (or the same kernels launched one by one) ----
+  StepGraph* sg = nullptr;
+  m->last_used_graph = 0;
+  if (get_flag("step_graph") && !profiling_enabled()) {
+    uint8_t* base = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(workspace), 1024));
+    sg = step_graph_for(m, w, base, batch, l_img, l_txt);
+  }
+  if (sg) {
+    for (int s = 0; s < steps; ++s) {
+      FB_CHECK_CUDA(cudaGraphLaunch(sg->exec, st));
+      count_launch_bulk(sg->launches, +1);
+    }
+    m->last_used_graph = 1;
+  } else {
+    for (int s = 0; s < steps; ++s) {
+      if (int rc = step_core(m, w, w.lat, nullptr, w.lat, w.step, batch, l_img, l_txt, st)) return rc;
+      if (int rc = launch_step_advance(w.step, st)) return rc;
+    }
+  }
+  if (int rc = launch_copy_rows(img, 0, w.lat, 0, lat_bytes, 1, st)) return rc;
+  m->last_B = batch, m->last_limg = l_img, m->last_ltxt = l_txt, m->last_ws = w;
+  return 0;
+}
+
+int fluxb200_model_denoise_info(const fluxb200_model* m, int32_t* used_graph, const char** note) {
+  FB_REQUIRE(m, "denoise_info: null model");
+  if (used_graph) *used_graph = m->last_used_graph;
+  if (note) *note = m->graph_note.c_str();
   return 0;
 }
 
@@ -941,7 +1095,7 @@ int fluxb200_model_tap(fluxb200_model* m, int32_t which, void* out, uint64_t out
   switch (which) {
     case 0: src = w.vec, bytes = B * D * 2; break;
     case 1: src = w.img, bytes = B * li * D * 2; break;
-    case 2: src = w.txt, bytes = B * lt * D * 2; break;
+    case 2: src = m->cfg.num_layers > 0 ? w.txt : w.txt_cache, bytes = B * lt * D * 2; break;
     case 3: src = w.x, bytes = B * L * D * 2; break;
     case 4: src = w.pe_cos, bytes = B * L * 64 * 2; break;
     case 5: src = w.pe_sin, bytes = B * L * 64 * 2; break;

@@ -84,6 +84,8 @@ struct alignas(64) GemmProblemDev {
   const bf16* gate;
   const bf16* res;
   long long gate_bstride;
+  const int* step_ptr;  // denoising loop: device step counter; gate += *step_ptr * gate_step_stride
+  long long gate_step_stride;
   int rows_per_batch, bias_mode, has_alpha;
   float alpha;
   // quantised B operand (fused dequant producer): per member a map over the packed bytes and one over the
@@ -737,7 +739,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
         valid = grow < p.M;
       }
       const long long gate_off =
-          (p.gate != nullptr) ? (p.rows_per_batch > 0 ? grow / p.rows_per_batch : 0) * p.gate_bstride : 0;
+          (p.gate != nullptr) ? (p.rows_per_batch > 0 ? grow / p.rows_per_batch : 0) * p.gate_bstride +
+                                    (p.step_ptr ? *p.step_ptr * p.gate_step_stride : 0)
+                              : 0;
       const bf162 alpha2 = __float2bfloat162_rn(p.alpha);
       const int bias_mode = p.bias_mode;
 
@@ -824,12 +828,9 @@ int set_gemm_trace(long long* buf) {
   return 0;
 }
 
-int launch_gemm(const GemmDesc* descs, int count, cudaStream_t stream) {
-  FB_REQUIRE(count >= 1 && count <= MAX_PROBLEMS, "launch_gemm: 1..4 problems per launch");
-  static_assert(sizeof(GemmParams) < 32000, "kernel parameter block too large");
-  static bool attr_set = false;
-  static bool use_pair = true;
-  if (!attr_set) {
+int gemm_init_device() {
+  static DeviceOnce attr_once;
+  if (attr_once.need()) {
     FB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(GemmCfg<false>::SMEM)));
     FB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -838,8 +839,16 @@ int launch_gemm(const GemmDesc* descs, int count, cudaStream_t stream) {
                                        static_cast<int>(GemmCfg<true, true>::SMEM)));
     FB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(GemmCfg<true>::SMEM)));
-    attr_set = true;
+    attr_once.done();
   }
+  return 0;
+}
+
+int launch_gemm(const GemmDesc* descs, int count, cudaStream_t stream) {
+  FB_REQUIRE(count >= 1 && count <= MAX_PROBLEMS, "launch_gemm: 1..4 problems per launch");
+  static_assert(sizeof(GemmParams) < 32000, "kernel parameter block too large");
+  if (int rc = gemm_init_device()) return rc;
+  bool use_pair = true;
   use_pair = get_flag("gemm_pair") != 0;  // A/B switch (env FLUXB200_GEMM_SINGLE_CTA=1 or fluxb200_set_flag)
   bool quant_b = false;
   for (int i = 0; i < count; ++i) quant_b |= (descs[i].qb != nullptr);
@@ -1000,6 +1009,8 @@ int launch_gemm(const GemmDesc* descs, int count, cudaStream_t stream) {
     }
     p.bias = d.bias, p.bias_mode = d.bias_mode;
     p.gate = d.gate, p.gate_bstride = d.gate_bstride, p.rows_per_batch = d.rows_per_batch, p.res = d.res;
+    p.step_ptr = d.step_ptr, p.gate_step_stride = d.gate_step_stride;
+    if (d.step_ptr) FB_REQUIRE(d.gate_step_stride % 8 == 0, "launch_gemm: gate step stride alignment");
     p.alpha = d.alpha, p.has_alpha = (d.alpha != 1.0f);
     if (d.N % 8 == 0) FB_REQUIRE(d.ld0 % 8 == 0, "launch_gemm: ldo must be a multiple of 8");
   }

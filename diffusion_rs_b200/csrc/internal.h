@@ -46,8 +46,20 @@ int encode_tmap_2d_raw(CUtensorMap* out, const void* base, int elem_bytes, uint6
 
 int num_sms();
 
+// Per-DEVICE one-time initialisation guard (cudaFuncSetAttribute and friends are per-device state: a process that
+// drives several GPUs must run them once on each).  Usage: static DeviceOnce once; if (once.need()) { ...; once.done(); }
+struct DeviceOnce {
+  unsigned long long mask = 0;  // bit d: done on device d (accessed atomically)
+  bool need() const;
+  void done();
+};
+// bytes of launch accounting, adjusted by the step-graph replay (graph nodes are not launched through count_launch)
+void count_launch_bulk(const unsigned long long* per_kind, int sign);
+void snapshot_launches(unsigned long long* per_kind);
+bool profiling_enabled();
+
 // ---- launch accounting + optional per-kernel-class CUDA-event timing (bench.py roofline evidence) ----
-enum KernelKind { KK_GEMM = 0, KK_ATTN, KK_LN_MOD, KK_QKNORM_ROPE, KK_GEMV, KK_DEQUANT, KK_GROUPNORM, KK_MISC, KK_COUNT };
+enum KernelKind { KK_GEMM = 0, KK_ATTN, KK_LN_MOD, KK_QKNORM_ROPE, KK_DEQUANT, KK_GROUPNORM, KK_MISC, KK_COUNT };
 void count_launch(int kind, int n = 1);
 struct ProfScope {  // records an event pair around the launches issued in its lifetime when profiling is enabled
   ProfScope(int kind, double flops, double bytes, cudaStream_t stream);
@@ -90,6 +102,9 @@ struct GemmDesc {
   int64_t gate_bstride = 0;
   int rows_per_batch = 0;
   const bf16* res = nullptr;  // same ld as out0; may alias out0; may be used without gate (plain residual add)
+  // denoising loop: gate points into a [step][...] table; the kernel adds (*step_ptr) * gate_step_stride elements
+  const int* step_ptr = nullptr;
+  int64_t gate_step_stride = 0;
   // Fused QK RMS-norm + RoPE + head-major relayout for columns [0, 3*qk_H*128) (the q|k|v projection): instead of
   // out0 the epilogue writes Q, K, V [B, H, L, 128] directly (SelfAttention::qkv + apply_rope, model.rs:86-95, 399-427).
   // Row r belongs to batch r / rows_per_batch and token qk_loff + r % rows_per_batch.
@@ -144,6 +159,8 @@ inline cudaError_t launch_ex(void (*kern)(KArgs...), dim3 grid, dim3 block, size
 int get_flag(const char* name);
 // One persistent launch over up to 4 problems (grouped): img + txt streams share the machine.
 int launch_gemm(const GemmDesc* descs, int count, cudaStream_t stream);
+int gemm_init_device();       // per-device kernel attributes; also called lazily by launch_gemm
+int attention_init_device();  // same for launch_attention
 int set_gemm_trace(long long* buf);  // debug: device buffer of 64*4 int64 written by scheduling unit 0, or nullptr
 
 // ---- tcgen05 flash attention: q,k,v [B,H,L,128] bf16 -> out rows [B, L, H*128] split at L_split ----

@@ -10,6 +10,8 @@
 // HBM-bound: one thread expands 16 packed bytes (32 weights) with 128-bit loads/stores.
 #include <cuda_fp16.h>
 
+#include <algorithm>
+
 #include "internal.h"
 #include "kernels.h"
 #include "ptx.cuh"
@@ -156,6 +158,150 @@ int launch_dequant_int8(const int8_t* w, const float* scb, bf16* out, int col, l
   const unsigned grid = static_cast<unsigned>((n + 16 * 256 - 1) / (16 * 256));
   count_launch(KK_DEQUANT);
   dequant_int8_rowwise_kernel<bf16><<<grid, 256, 0, stream>>>(w, scb, out, col, n);
+  FB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Model path: every member of one fused Linear (q|k|v|proj_mlp ...) is expanded into the bf16 staging buffer by ONE
+// launch (blockIdx.y = member).  Fully coalesced: a thread reads 4 packed bytes and writes one 16-byte vector, so a warp
+// reads 128 contiguous bytes and writes 512 contiguous bytes per iteration; 4 independent iterations are in flight
+// per thread.  The 4-bit code books are expanded to a byte -> (first, second) value-pair table in shared memory
+// (the high nibble is the first weight, dequant.cu:155-156).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void q4k_scale_min(const uint8_t* sc, int is, float d, float dmin, float& s, float& m) {
+  uint32_t dd, mm;
+  if (is < 4) {
+    dd = sc[is] & 63;
+    mm = sc[is + 4] & 63;
+  } else {
+    dd = (sc[is + 4] & 0xF) | ((sc[is - 4] >> 6) << 4);
+    mm = (sc[is + 4] >> 4) | ((sc[is] >> 6) << 4);
+  }
+  s = __fmul_rn(d, static_cast<float>(dd));
+  m = __fmul_rn(dmin, static_cast<float>(mm));
+}
+
+__global__ void __launch_bounds__(256) dequant_batch_kernel(const DequantBatch batch) {
+  __shared__ float2 lut2[256];
+  const DequantJob& j = batch.job[blockIdx.y];
+  if (j.kind == QB_NF4 || j.kind == QB_FP4) {
+    const float* cb = j.kind == QB_NF4 ? kNF4 : kFP4;
+    lut2[threadIdx.x] = make_float2(cb[threadIdx.x >> 4], cb[threadIdx.x & 15]);
+    __syncthreads();
+    // unit = 4 packed bytes -> 8 weights (16 bytes of bf16)
+    const long long units = j.n / 8;
+    const int bs_units = j.blocksize / 8;  // units per absmax entry (blocksize is a power of two >= 64)
+    constexpr int IT = 4;
+    const long long base = static_cast<long long>(blockIdx.x) * (256 * IT) + threadIdx.x;
+    uint32_t pk[IT];
+    float am[IT];
+#pragma unroll
+    for (int it = 0; it < IT; ++it) {
+      const long long u = base + it * 256;
+      pk[it] = u < units ? __ldg(reinterpret_cast<const uint32_t*>(j.packed) + u) : 0u;
+      am[it] = u < units ? __ldg(j.absmax + u / bs_units) : 0.f;
+    }
+#pragma unroll
+    for (int it = 0; it < IT; ++it) {
+      const long long u = base + it * 256;
+      if (u >= units) break;
+      uint4 o;
+      float2 c;
+      c = lut2[pk[it] & 0xffu];         o.x = pack_bf16(c.x * am[it], c.y * am[it]);
+      c = lut2[(pk[it] >> 8) & 0xffu];  o.y = pack_bf16(c.x * am[it], c.y * am[it]);
+      c = lut2[(pk[it] >> 16) & 0xffu]; o.z = pack_bf16(c.x * am[it], c.y * am[it]);
+      c = lut2[pk[it] >> 24];           o.w = pack_bf16(c.x * am[it], c.y * am[it]);
+      reinterpret_cast<uint4*>(j.out)[u] = o;
+    }
+  } else if (j.kind == QB_INT8) {
+    // unit = 8 int8 weights -> 16 bytes of bf16
+    const long long units = j.n / 8;
+    const int col_units = j.col / 8;
+    constexpr int IT = 4;
+    const long long base = static_cast<long long>(blockIdx.x) * (256 * IT) + threadIdx.x;
+#pragma unroll
+    for (int it = 0; it < IT; ++it) {
+      const long long u = base + it * 256;
+      if (u >= units) break;
+      const uint2 q = __ldg(reinterpret_cast<const uint2*>(j.packed) + u);
+      const float sc = __ldg(j.scb + u / col_units);
+      const uint32_t w2[2] = {q.x, q.y};
+      uint32_t o[4];
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        const int v0 = static_cast<int8_t>((w2[h >> 1] >> (16 * (h & 1))) & 0xffu);
+        const int v1 = static_cast<int8_t>((w2[h >> 1] >> (16 * (h & 1) + 8)) & 0xffu);
+        o[h] = pack_bf16((static_cast<float>(v0) * sc) / 127.f, (static_cast<float>(v1) * sc) / 127.f);
+      }
+      reinterpret_cast<uint4*>(j.out)[u] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  } else {
+    // Q4_K: unit = one 64-weight group (32 q bytes): 8 lanes, each 4 q bytes -> 4 low-nibble + 4 high-nibble weights.
+    // blockIdx.x covers 1024 lane-units = 32 super-blocks.
+    const long long nblocks = j.n / 256;
+    constexpr int IT = 4;
+    const long long base = static_cast<long long>(blockIdx.x) * (256 * IT) + threadIdx.x;
+#pragma unroll
+    for (int it = 0; it < IT; ++it) {
+      const long long u = base + it * 256;  // lane-unit: super-block u / 32, lane u % 32
+      const long long blk = u >> 5;
+      if (blk >= nblocks) break;
+      const int lane = static_cast<int>(u & 31);
+      const uint8_t* p = j.packed + blk * 144;
+      const float d = __half2float(*reinterpret_cast<const __half*>(p));
+      const float dmin = __half2float(*reinterpret_cast<const __half*>(p + 2));
+      const int g = lane >> 3, off = (lane & 7) * 4;
+      float d1, m1, d2, m2;
+      q4k_scale_min(p + 4, 2 * g, d, dmin, d1, m1);
+      q4k_scale_min(p + 4, 2 * g + 1, d, dmin, d2, m2);
+      const uint32_t q4 = *reinterpret_cast<const uint32_t*>(p + 16 + g * 32 + off);
+      bf16* o = j.out + blk * 256 + g * 64 + off;
+      float lo[4], hi[4];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const uint32_t q = (q4 >> (8 * b)) & 0xff;
+        lo[b] = __half2float(__float2half_rn(__fsub_rn(__fmul_rn(d1, static_cast<float>(q & 0xF)), m1)));
+        hi[b] = __half2float(__float2half_rn(__fsub_rn(__fmul_rn(d2, static_cast<float>(q >> 4)), m2)));
+      }
+      uint2 v;
+      v.x = pack_bf16(lo[0], lo[1]), v.y = pack_bf16(lo[2], lo[3]);
+      *reinterpret_cast<uint2*>(o) = v;
+      v.x = pack_bf16(hi[0], hi[1]), v.y = pack_bf16(hi[2], hi[3]);
+      *reinterpret_cast<uint2*>(o + 32) = v;
+    }
+  }
+}
+
+int launch_dequant_batch(const DequantBatch& batch, cudaStream_t stream) {
+  FB_REQUIRE(batch.count >= 1 && batch.count <= DequantBatch::MAX, "dequant_batch: 1..4 members");
+  long long max_units = 0;
+  double bytes = 0;
+  for (int i = 0; i < batch.count; ++i) {
+    const DequantJob& j = batch.job[i];
+    FB_REQUIRE(j.packed && j.out && j.n > 0, "dequant_batch: null member");
+    FB_REQUIRE((reinterpret_cast<uintptr_t>(j.packed) & 15) == 0 && (reinterpret_cast<uintptr_t>(j.out) & 15) == 0,
+               "dequant_batch: 16-byte alignment");
+    long long units = 0;
+    if (j.kind == QB_NF4 || j.kind == QB_FP4) {
+      FB_REQUIRE(j.absmax && j.blocksize >= 64 && (j.blocksize & (j.blocksize - 1)) == 0 && j.n % j.blocksize == 0,
+                 "dequant_batch: 4-bit members need absmax and a power-of-two blocksize >= 64 dividing the weight");
+      units = j.n / 8, bytes += 2.5 * j.n + 4.0 * j.n / j.blocksize;
+    } else if (j.kind == QB_INT8) {
+      FB_REQUIRE(j.scb && j.col % 8 == 0, "dequant_batch: int8 members need SCB and K % 8 == 0");
+      units = j.n / 8, bytes += 3.0 * j.n;
+    } else if (j.kind == QB_Q4K) {
+      FB_REQUIRE(j.n % 256 == 0, "dequant_batch: Q4_K element count must be a multiple of 256");
+      units = j.n / 8, bytes += 2.5625 * j.n;  // 32 lane-units per 256 weights
+    } else {
+      return fail("dequant_batch: bad kind");
+    }
+    max_units = std::max(max_units, units);
+  }
+  ProfScope _ps(KK_DEQUANT, 0, bytes, stream);
+  count_launch(KK_DEQUANT);
+  const dim3 grid(static_cast<unsigned>((max_units + 1023) / 1024), batch.count);
+  dequant_batch_kernel<<<grid, 256, 0, stream>>>(batch);
   FB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -109,6 +109,11 @@ def flux_config_from_json(j: dict):
 
 def vae_config_from_json(j: dict):
     from .vae import VaeConfig
+    # AutoEncoderKl::decode applies post_quant_conv first when the config asks for it (autoencoder_kl.rs:78-96,
+    # 112-119); FLUX's VAE does not use it and the decoder here has no 1x1 conv for it: refuse rather than decode wrong
+    if j.get("use_post_quant_conv", False) or j.get("use_quant_conv", False):
+        raise L.Fluxb200Error("VAE configs with use_quant_conv / use_post_quant_conv are not supported "
+                              "(FLUX.1's autoencoder sets both to false)")
     return VaeConfig(latent_channels=j["latent_channels"], out_channels=j["out_channels"],
                      block_out_channels=tuple(j["block_out_channels"]), layers_per_block=j["layers_per_block"],
                      norm_num_groups=j["norm_num_groups"],

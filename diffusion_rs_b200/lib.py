@@ -48,6 +48,8 @@ SIGNATURES = {
                                            c_void_p]),
     "fluxb200_model_finalize": (c_int, [c_void_p, c_void_p]),
     "fluxb200_model_workspace_size": (c_int, [c_void_p, c_int, c_int, c_int, C.POINTER(C.c_uint64)]),
+    "fluxb200_model_denoise_workspace_size": (c_int, [c_void_p, c_int, c_int, c_int, c_int, C.POINTER(C.c_uint64)]),
+    "fluxb200_model_denoise_info": (c_int, [c_void_p, C.POINTER(c_int), C.POINTER(C.c_char_p)]),
     "fluxb200_model_forward": (c_int, [c_void_p] + [c_void_p] * 8 + [c_int, c_int, c_int, c_void_p, C.c_uint64,
                                                                       c_void_p]),
     "fluxb200_model_denoise": (c_int, [c_void_p] + [c_void_p] * 5 + [c_float, C.POINTER(C.c_double), c_int, c_int,

@@ -6,7 +6,8 @@ What is B200-native here is the denoising hot path (`FluxPipeline::forward`, pip
 noise latents to the u8 image) and, as the first widening step, the two text encoders in front
 of it (T5 / CLIP, text_encoders.py).  A prompt is one of: `PromptEmbeds` (encoder outputs computed elsewhere),
 `PromptTokens` (token ids -> the encoders run on the GPU), or a string (tokenised when the snapshot ships its
-tokenizers, otherwise mapped to deterministic synthetic embeddings so the API stays runnable without weights or network).
+tokenizers; for `ModelSource.synthetic` pipelines only - random-init weights - mapped to deterministic synthetic
+embeddings so the API stays runnable without weights or network; anything else raises).
 Multi-GPU: one process per GPU; prompts are sharded across ranks (independent trajectories — no per-step collective);
 the only NCCL traffic is the weight broadcast at load.
 """
@@ -126,6 +127,19 @@ def calculate_shift(image_seq_len, base_seq_len, max_seq_len, base_shift, max_sh
     return image_seq_len * m + b
 
 
+def shift_seq_len(noise_shape, mode: str = "reference") -> int:
+    """The `image_seq_len` FluxPipeline::forward feeds to calculate_shift.  The reference passes `img.dims()[1]` of the
+    UNPACKED noise [bs, 16, h, w] (pipelines/flux/mod.rs:279, `img` is only packed inside State::new), i.e. the latent
+    channel count 16 whatever the resolution -> mu = 0.4594 and one sigma schedule for every image size.  BFL / diffusers
+    pass the packed sequence length (h/2)*(w/2) (mu = 1.15 at 1024^2).  A drop-in mirrors the reference ("reference",
+    the default); "bfl" selects the upstream-FLUX behaviour."""
+    if mode == "reference":
+        return int(noise_shape[1])
+    if mode == "bfl":
+        return (int(noise_shape[2]) // 2) * (int(noise_shape[3]) // 2)
+    raise L.Fluxb200Error(f"unknown shift mode {mode!r} (reference | bfl)")
+
+
 def latent_hw(height: int, width: int) -> tuple[int, int]:  # get_noise flux/sampling.rs:11-12
     return (height + 15) // 16 * 2, (width + 15) // 16 * 2
 
@@ -170,9 +184,12 @@ class Pipeline:
     """`diffusion_rs_core::Pipeline` (pipelines/mod.rs:110-270)."""
 
     def __init__(self, transformer: FluxTransformer, vae: AutoEncoderKl, scheduler: SchedulerConfig, is_dev: bool,
-                 t5: T5EncoderModel | None = None, clip: ClipTextTransformer | None = None, tokenizers=None):
+                 t5: T5EncoderModel | None = None, clip: ClipTextTransformer | None = None, tokenizers=None,
+                 synthetic: bool = False):
         self.transformer, self.vae, self.scheduler, self.is_dev = transformer, vae, scheduler, is_dev
         self.t5, self.clip, self.tokenizers = t5, clip, tokenizers
+        self.synthetic = synthetic      # random-init weights: string prompts map to deterministic synthetic embeddings
+        self.shift_mode = "reference"   # see shift_seq_len
         self.max_batch = 4  # images per denoise call on one GPU
         self._pinned = {}
 
@@ -266,7 +283,7 @@ class Pipeline:
             t5.finalize()
             clip.finalize()
         torch.cuda.synchronize()
-        return cls(tr, va, sched, is_dev, t5, clip)
+        return cls(tr, va, sched, is_dev, t5, clip, synthetic=(source.kind == "synthetic"))
 
     # -- helpers ------------------------------------------------------------------------------------------------------
     def text_len(self) -> int:
@@ -285,12 +302,13 @@ class Pipeline:
         normaliser, no pre-tokeniser, no BOS/EOS, merges read from line 2 on; mirrored as is)."""
         if tok_bytes is None:
             return None
+        import json as _json
         try:
-            import json as _json
             from tokenizers import Tokenizer
             from tokenizers.models import BPE
-        except ImportError:
-            return None
+        except ImportError as e:  # the snapshot ships tokenizer files: not being able to read them is an error
+            raise L.Fluxb200Error("the snapshot ships tokenizers but the `tokenizers` package is not importable; "
+                                  "install it or pass PromptTokens / PromptEmbeds") from e
         t5_tok = Tokenizer.from_str(tok_bytes["t5"].decode())
         vocab = _json.loads(tok_bytes["clip_vocab"].decode())
         merges = [tuple(x.split(" ")) for x in tok_bytes["clip_merges"].decode().split("\n")[1:]]
@@ -349,6 +367,10 @@ class Pipeline:
         if tok_idx:
             for i, e in zip(tok_idx, self.encode_prompts([prompts[i] for i in tok_idx])):
                 prompts[i] = e
+        if any(isinstance(p, str) for p in prompts) and not self.synthetic:
+            # a real checkpoint must never answer a text prompt with an image of random embeddings
+            raise L.Fluxb200Error("this pipeline cannot encode text prompts (no tokenizers / text encoders in the "
+                                  "snapshot); pass PromptTokens or PromptEmbeds")
         embeds = [p if isinstance(p, PromptEmbeds) else self.synthetic_embeds(p) for p in prompts]
         n = len(embeds)
         h, w = latent_hw(params.height, params.width)
@@ -397,7 +419,8 @@ class Pipeline:
         img_ids = img_ids1[None].repeat(B, 1, 1).contiguous().cuda()
         txt_ids = txt_ids1[None].repeat(B, 1, 1).contiguous().cuda()
         sc = self.scheduler
-        mu = calculate_shift(l_img, sc.base_image_seq_len, sc.max_image_seq_len, sc.base_shift, sc.max_shift)
+        mu = calculate_shift(shift_seq_len(noise.shape, self.shift_mode), sc.base_image_seq_len, sc.max_image_seq_len,
+                             sc.base_shift, sc.max_shift)
         timesteps = sc.get_timesteps(params.num_steps, mu)
         self.transformer.denoise(img, img_ids, txt, txt_ids, vec, params.guidance_scale, timesteps)
         out_d = self.vae.decode_packed_u8(img, h2, w2)  # [B, 16*h2, 16*w2, 3] u8

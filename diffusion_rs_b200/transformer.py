@@ -71,9 +71,13 @@ class FluxTransformer:
         return m
 
     # -- workspace (caller-owned, as every activation buffer) --------------------------------------------
-    def workspace(self, B: int, l_img: int, l_txt: int) -> torch.Tensor:
+    def workspace(self, B: int, l_img: int, l_txt: int, n_timesteps: int | None = None) -> torch.Tensor:
         n = C.c_uint64()
-        L.check(self._lib.fluxb200_model_workspace_size(self._h, B, l_img, l_txt, C.byref(n)))
+        if n_timesteps is None:
+            L.check(self._lib.fluxb200_model_workspace_size(self._h, B, l_img, l_txt, C.byref(n)))
+        else:  # the denoising loop keeps the per-step tables of the whole image in the workspace
+            L.check(self._lib.fluxb200_model_denoise_workspace_size(self._h, B, l_img, l_txt, n_timesteps,
+                                                                    C.byref(n)))
         if self._ws is None or self._ws.numel() < n.value:
             self._ws = None
             self._ws = torch.empty(n.value, dtype=torch.uint8, device="cuda")
@@ -103,13 +107,19 @@ class FluxTransformer:
         """In-place Euler loop over `timesteps` on img [B,l_img,64]."""
         B, l_img, _ = img.shape
         l_txt = txt.shape[1]
-        ws = self.workspace(B, l_img, l_txt)
+        ws = self.workspace(B, l_img, l_txt, len(timesteps))
         ts = (C.c_double * len(timesteps))(*timesteps)
         L.check(self._lib.fluxb200_model_denoise(self._h, img.data_ptr(), img_ids.data_ptr(), txt.data_ptr(),
                                                  txt_ids.data_ptr(), y.data_ptr(), float(guidance_scale), ts,
                                                  len(timesteps), B, l_img, l_txt, ws.data_ptr(), ws.numel(),
                                                  L.current_stream()))
         return img
+
+    def denoise_info(self) -> tuple[bool, str]:
+        """(steps of the last denoise were CUDA-graph replays, note explaining why not)."""
+        used, note = C.c_int32(0), C.c_char_p()
+        L.check(self._lib.fluxb200_model_denoise_info(self._h, C.byref(used), C.byref(note)))
+        return bool(used.value), (note.value or b"").decode()
 
     def tap(self, which: int, shape) -> torch.Tensor:
         out = torch.empty(*shape, device="cuda", dtype=torch.bfloat16)

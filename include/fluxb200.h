@@ -148,6 +148,11 @@ int fluxb200_model_finalize(fluxb200_model* m, fluxb200_stream_t stream);
 int fluxb200_model_workspace_size(const fluxb200_model* m, int32_t batch, int32_t l_img, int32_t l_txt,
                                   uint64_t* bytes);
 
+/* Bytes of caller-owned workspace fluxb200_model_denoise needs: the forward workspace plus the per-step tables of the
+ * whole loop (vec_ and every AdaLN modulation vector of all n_timesteps - 1 steps are projected before the loop). */
+int fluxb200_model_denoise_workspace_size(const fluxb200_model* m, int32_t batch, int32_t l_img, int32_t l_txt,
+                                          int32_t n_timesteps, uint64_t* bytes);
+
 /* Flux::forward (model.rs:790-833).  All tensors are device pointers:
  *   img bf16 [B,l_img,64]; img_ids bf16 [B,l_img,3]; txt bf16 [B,l_txt,4096]; txt_ids bf16 [B,l_txt,3];
  *   timesteps f32 [B]; y bf16 [B,768]; guidance f32 [B] or NULL; out bf16 [B,l_img,64]. */
@@ -157,11 +162,21 @@ int fluxb200_model_forward(fluxb200_model* m, const void* img, const void* img_i
                            uint64_t workspace_bytes, fluxb200_stream_t stream);
 
 /* Sampler::sample (pipelines/sampling.rs:25-48): the Euler flow-matching loop over `timesteps` (host f64[n_t]),
- * updating `img` in place; txt projection and the RoPE table are hoisted out of the loop (they do not depend on t). */
+ * updating `img` in place.  Everything that does not depend on the evolving latent is hoisted out of the loop (RoPE
+ * table, txt projection, vec_ and all modulation projections of every step); one step is captured as a CUDA graph
+ * (cached per workspace address / geometry in the handle) and replayed n_t - 1 times, the Euler update being the
+ * epilogue of the step's last GEMM.  Nothing here synchronises: `timesteps` is consumed before the call returns (the
+ * scalars travel as kernel parameters) and all work is enqueued on `stream`.
+ * workspace: fluxb200_model_denoise_workspace_size bytes. */
 int fluxb200_model_denoise(fluxb200_model* m, void* img, const void* img_ids, const void* txt, const void* txt_ids,
                            const void* y, float guidance_scale, const double* timesteps, int32_t n_timesteps,
                            int32_t batch, int32_t l_img, int32_t l_txt, void* workspace, uint64_t workspace_bytes,
                            fluxb200_stream_t stream);
+
+/* After fluxb200_model_denoise: *used_graph = 1 if the steps were CUDA-graph replays, 0 if the kernels were launched
+ * one by one ("step_graph" flag off, profiling on, or capture unavailable - *note then says why).  Either pointer may
+ * be NULL. */
+int fluxb200_model_denoise_info(const fluxb200_model* m, int32_t* used_graph, const char** note);
 
 /* Debug / parity taps: copy an internal activation of the last forward into `out` (device, bf16).
  * which: 0 = vec_ [B,3072], 1 = img stream after the double blocks [B,l_img,3072], 2 = txt stream [B,l_txt,3072],
@@ -278,6 +293,8 @@ int fluxb200_clip_forward(fluxb200_clip* m, const int32_t* ids, void* hidden_out
  *                    L2-sized bf16 staging buffer (default 0: at M = 4608 tokens per weight the staged path is faster)
  *   "attn_variant"   build of the attention kernel, see attention.cu (default 0; FLUXB200_ATTN_VARIANT=n)
  *   "pdl"            programmatic dependent launch for GEMM / attention / LN-modulate (default 1; FLUXB200_PDL=0)
+ *   "step_graph"     fluxb200_model_denoise replays one captured CUDA graph per step (default 1; FLUXB200_STEP_GRAPH=0)
+ *   "gemm_big"       512x256-per-CTA-pair tiles for the long-K GEMMs (default 1; FLUXB200_GEMM_BIG=0)
  * FLUXB200_GEMM_MAX_UNITS=n limits the pair GEMM to n CTA pairs (experiments only). */
 int fluxb200_set_flag(const char* name, int value);
 void fluxb200_profile_enable(int on);

@@ -95,6 +95,35 @@ def test_scheduler_matches_oracle():
         P.SchedulerConfig().get_timesteps(4, None)
 
 
+def test_shift_call_site_mirrors_the_reference():
+    """FluxPipeline::forward passes `img.dims()[1]` of the UNPACKED noise [bs,16,h,w] to calculate_shift
+    (pipelines/flux/mod.rs:276-285): image_seq_len = 16 at every resolution.  The default mirrors that; "bfl" is the
+    packed sequence length upstream FLUX uses."""
+    from diffusion_rs_b200 import lib as L
+    from diffusion_rs_b200 import pipeline as P
+    sc = P.SchedulerConfig()
+    for hw in ((128, 128), (90, 160), (32, 32)):
+        shape = (3, 16) + hw
+        assert P.shift_seq_len(shape) == P.shift_seq_len(shape, "reference") == 16
+        assert P.shift_seq_len(shape, "bfl") == (hw[0] // 2) * (hw[1] // 2)
+    mu = P.calculate_shift(16, sc.base_image_seq_len, sc.max_image_seq_len, sc.base_shift, sc.max_shift)
+    assert abs(mu - (0.5 + (16 - 256) * (1.15 - 0.5) / (4096 - 256))) < 1e-12 and abs(mu - 0.459375) < 1e-9
+    ts = sc.get_timesteps(50, mu)
+    assert ts[0] == 1.0 and ts[-1] == 0.0 and all(a > b for a, b in zip(ts, ts[1:]))
+    with pytest.raises(L.Fluxb200Error):
+        P.shift_seq_len((1, 16, 8, 8), "nope")
+
+
+def test_vae_config_rejects_quant_convs():
+    from diffusion_rs_b200 import ingest
+    from diffusion_rs_b200 import lib as L
+    base = dict(latent_channels=16, out_channels=3, block_out_channels=[128, 256, 512, 512], layers_per_block=2,
+                norm_num_groups=32, scaling_factor=0.3611, shift_factor=0.1159)
+    assert ingest.vae_config_from_json(dict(base, use_post_quant_conv=False)).latent_channels == 16
+    with pytest.raises(L.Fluxb200Error):
+        ingest.vae_config_from_json(dict(base, use_post_quant_conv=True))
+
+
 def test_patchify_ids_latent_geometry():
     from diffusion_rs_b200 import pipeline as P
     from oracle import flux as OF

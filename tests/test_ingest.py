@@ -129,10 +129,14 @@ def test_pipeline_load_from_local_directory(tmp_path, fluxlib):
     src.num_layers, src.num_single_layers = 1, 1
     p2 = Pipeline.load(src)
     params = DiffusionGenerationParams(height=64, width=96, num_steps=2, guidance_scale=3.5)
-    a = p1.forward(["a cat"], params)
-    b = p2.forward(["a cat"], params)
+    emb = [p1.synthetic_embeds("a cat")]
+    a = p1.forward(emb, params)
+    b = p2.forward(emb, params)
     assert a[0].shape == (64, 96, 3) and a[0].dtype == torch.uint8
     assert torch.equal(a[0], b[0])
+    # a real snapshot without tokenizers / text encoders must refuse a text prompt instead of inventing embeddings
+    with pytest.raises(L.Fluxb200Error):
+        p1.forward(["a cat"], params)
 
 
 @pytest.mark.gpu
