@@ -88,10 +88,11 @@ FB_DEVICE void ex2_poly2(float& y0, float& y1, float x0, float x1) {
 // pairs, 16 scores (8 packed columns = one k-step of O += P.V) at a time, and published to the MMA thread in NHAND
 // instalments so that most of P.V runs under the remaining exponentials.  The wait for an instalment's TMEM stores
 // is issued one chunk late (after the next chunk's arithmetic), so the MUFU never idles behind tcgen05.wait::st.
-//   POLY_MOD  every POLY_MOD-th PAIR of exponentials is evaluated on the FMA pipe (ex2_poly2) instead of the MUFU
-//             unit (0 = all on MUFU).  Measured (scripts/ubench/exp_rate.cu): a 128x128 tile costs 1600 clk with all
-//             exponentials on the MUFU (16/clk/SM) and 1080 clk with every 4th pair on the FMA pipe.
-template <int POLY_MOD, int NHAND, int NCH, class Arrive>
+//   POLY_MASK bit i set: the i-th PAIR of every group of 8 pairs is evaluated on the FMA pipe (ex2_poly2) instead of the
+//             MUFU unit (0 = all on MUFU, 0x88 = every 4th pair, 0xAA = every other pair).  Measured
+//             (scripts/ubench/exp_rate.cu): a 128x128 tile costs 1600 clk with all exponentials on the MUFU (16/clk/SM)
+//             and 1080 clk with every 4th pair on the FMA pipe.
+template <int POLY_MASK, int NHAND, int NCH, class Arrive>
 FB_DEVICE void softmax_exp_store(uint32_t (&s)[NCH * 16], uint32_t tP, float sl2, float nmb, float& l_run, int lane,
                                  Arrive&& arrive) {
   constexpr int CH = NCH / NHAND;  // chunks per instalment
@@ -103,7 +104,7 @@ FB_DEVICE void softmax_exp_store(uint32_t (&s)[NCH * 16], uint32_t tP, float sl2
     for (int i = 0; i < 8; ++i) {
       float x0, x1, p0, p1;
       ffma2(x0, x1, __uint_as_float(s[c * 16 + 2 * i]), __uint_as_float(s[c * 16 + 2 * i + 1]), sl2, sl2, nmb, nmb);
-      if (POLY_MOD > 0 && (i % (POLY_MOD > 0 ? POLY_MOD : 1) == POLY_MOD - 1)) {
+      if ((POLY_MASK >> i) & 1) {
         ex2_poly2(p0, p1, x0, x1);
       } else {
         p0 = ex2_approx(x0);
@@ -135,7 +136,7 @@ FB_DEVICE void softmax_exp_store(uint32_t (&s)[NCH * 16], uint32_t tP, float sl2
 //                 "Data is ready" barriers live in the leader CTA (remote arrivals, 2-SM TMA), "data has been
 //                 consumed" barriers are signalled in both CTAs by multicast commits.
 // Other knobs (selected at run time through the "attn_variant" flag; see launch_attention):
-//   POLY_MOD  see softmax_exp_store.
+//   POLY_MASK see softmax_exp_store.
 //   NHAND     number of instalments in which P is handed to the MMA thread (1, 2 or 4).
 //   PP        ping-pong the two query tiles on the MUFU through a pair of named barriers.
 //   RPT       threads per query row (1 or 2).  With 2, warps w and w+4 of a tile share a TMEM lane quarter and split the
@@ -155,7 +156,7 @@ struct AttnCfg {
   static constexpr size_t SMEM = XCH_OFF + 2 * 2 * 2 * 128 * sizeof(float);
 };
 
-template <bool PAIR, int POLY_MOD, int NHAND, bool PP, int RPT, bool TRACE>
+template <bool PAIR, int POLY_MASK, int NHAND, bool PP, int RPT, bool TRACE>
 __global__ void __launch_bounds__((8 * RPT + 4) * 32, 1) attention_tcgen05_kernel(const __grid_constant__ AttnParams P) {
   static_assert(RPT == 1 || (RPT == 2 && NHAND == 1), "two threads per row hand P over in one piece");
   constexpr int NSW = 4 * RPT;        // softmax warps per tile
@@ -458,7 +459,7 @@ __global__ void __launch_bounds__((8 * RPT + 4) * 32, 1) attention_tcgen05_kerne
       if (TRACE && tr && j < 64) tr[(j * 2 + g) * 8 + 2] = clock64();
       if (PP) named_bar_sync(1 + g, SM_THREADS);  // wait for this tile's turn on the MUFU
       if (TRACE && tr && j < 64) tr[(j * 2 + g) * 8 + 3] = clock64();
-      softmax_exp_store<POLY_MOD, NHAND, COLS / 16>(s, tP, sl2, nmb, l_run, lane, arrive_p);
+      softmax_exp_store<POLY_MASK, NHAND, COLS / 16>(s, tP, sl2, nmb, l_run, lane, arrive_p);
       if (TRACE && tr && j < 64) tr[(j * 2 + g) * 8 + 4] = clock64();
       if (PP) named_bar_arrive(2 - g, SM_THREADS);  // hand the MUFU to the other tile
       tc_wait_st();
@@ -530,13 +531,19 @@ struct AttnVariant {
    attention_tcgen05_kernel<PAIR, POLY, NHAND, PP, RPT, true>, PAIR ? 1 : 0, (8 * RPT + 4) * 32, WHAT}
 // run-time selectable builds of the kernel ("attn_variant" flag); index 0 is the production default
 static const AttnVariant kAttnVariants[] = {
-    FB_ATTN_VARIANT(false, 4, 1, true, 1, "1 CTA, every 4th exp2 pair on the FMA pipe, whole-P handoff (production)"),
+    FB_ATTN_VARIANT(false, 0x88, 1, true, 1, "1 CTA, every 4th exp2 pair on the FMA pipe, whole-P handoff"),
     FB_ATTN_VARIANT(false, 0, 1, true, 1, "1 CTA, all exp2 on the MUFU"),
-    FB_ATTN_VARIANT(false, 4, 4, true, 1, "1 CTA, poly 1/4, P in 4 instalments"),
-    FB_ATTN_VARIANT(true, 4, 1, true, 1, "CTA pair, poly 1/4"),
-    FB_ATTN_VARIANT(false, 4, 1, true, 2, "1 CTA, 2 threads per row, poly 1/4"),
+    FB_ATTN_VARIANT(false, 0x88, 4, true, 1, "1 CTA, poly 1/4, P in 4 instalments"),
+    FB_ATTN_VARIANT(true, 0x88, 1, true, 1, "CTA pair, poly 1/4"),
+    FB_ATTN_VARIANT(false, 0x88, 1, true, 2, "1 CTA, 2 threads per row, poly 1/4"),
+    FB_ATTN_VARIANT(false, 0xAA, 1, true, 1, "1 CTA, every other exp2 pair on the FMA pipe"),
+    FB_ATTN_VARIANT(false, 0x92, 1, true, 1, "1 CTA, 3 of 8 exp2 pairs on the FMA pipe"),
+    FB_ATTN_VARIANT(false, 0xDA, 1, true, 1, "1 CTA, 5 of 8 exp2 pairs on the FMA pipe"),
+    FB_ATTN_VARIANT(false, 0xAA, 1, false, 1, "1 CTA, poly 1/2, no MUFU ping-pong"),
 };
 static constexpr int kNumAttnVariants = sizeof(kAttnVariants) / sizeof(kAttnVariants[0]);
+
+int attention_num_variants() { return kNumAttnVariants; }
 
 int attention_init_device() {
   static DeviceOnce attr_once;

@@ -50,8 +50,14 @@ int fluxb200_linear_quant(const void* a, int64_t lda, const void* packed, const 
   return launch_gemm(&d, 1, static_cast<cudaStream_t>(stream));
 }
 
+int fluxb200_attn_variants(void) { return attention_num_variants(); }
+
 int fluxb200_sdpa(const void* q, const void* k, const void* v, void* out, int32_t B, int32_t H, int32_t L,
-                  float scale, fluxb200_stream_t stream) {
+                  int32_t head_dim, float scale, float softcapping, fluxb200_stream_t stream) {
+  // ops::sdpa(q, k, v, scale, softcapping) (diffusion_rs_backend/src/ops.rs:247-262): the flash kernel covers what the
+  // FLUX path calls it with; anything else must go to the stock path (the caller checks the status and falls through)
+  FB_REQUIRE(head_dim == 128, "sdpa: only head_dim 128 is implemented (FLUX); use the stock ops::sdpa otherwise");
+  FB_REQUIRE(softcapping == 1.0f, "sdpa: softcapping != 1.0 is not implemented; use the stock ops::sdpa");
   AttnDesc d;
   d.q = static_cast<const bf16*>(q), d.k = static_cast<const bf16*>(k), d.v = static_cast<const bf16*>(v);
   d.B = B, d.H = H, d.L = L, d.scale = scale;

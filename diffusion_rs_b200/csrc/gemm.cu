@@ -107,6 +107,9 @@ struct GemmParams {
   GemmProblemDev p[MAX_PROBLEMS];
   int count;
   int total_tiles;
+  // BIG kernel: tile_begin / sched_m of the problems count 512-row "positions"; the first n_big positions are computed
+  // as 512x256 tiles, the remaining ones as their two 256x256 halves; total_items = n_big + 2 * (positions - n_big)
+  int n_big, total_items;
   long long* trace;  // debug (fluxb200_debug_gemm_trace): per tile of scheduling unit 0, clock64 waits of the MMA thread
 };
 
@@ -475,6 +478,86 @@ __device__ __forceinline__ void dequant_producer(const GemmParams& P, uint8_t* s
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Epilogue of one 128-row x 256-column accumulator (TMEM columns [t_acc, t_acc + 256)) by the calling warp: lane quarter
+// q = warp % 4 (hardware rule), column half chosen by the warp's index (8 epilogue warps) or both halves in turn (4).
+// The caller has waited for the accumulator; it releases it afterwards.
+// ------------------------------------------------------------------------------------------------
+template <int EPI_WARPS, bool QKROPE = true>
+__device__ __forceinline__ void epi_drain(const GemmProblemDev& p, int n_t, int m_t, uint32_t t_acc, int warp, int lane) {
+  const int q = warp & 3;
+  const int r = q * 32 + lane;  // row inside the tile == TMEM lane
+  long long grow;
+  bool valid;
+  if (p.conv) {
+    int per_img = p.tiles_h * p.tiles_w;
+    int cn = m_t / per_img;
+    int rem = m_t - cn * per_img;
+    int h = (rem / p.tiles_w) * CONV_TH + r / CONV_TW;
+    int w = (rem % p.tiles_w) * CONV_TW + r % CONV_TW;
+    valid = (m_t < p.tiles_m) && (h < p.cH) && (w < p.cW);
+    grow = (static_cast<long long>(cn) * p.cH + h) * p.cW + w;
+  } else {
+    grow = static_cast<long long>(m_t) * BLOCK_M + r;
+    valid = grow < p.M;
+  }
+  const long long gate_off =
+      (p.gate != nullptr) ? (p.rows_per_batch > 0 ? grow / p.rows_per_batch : 0) * p.gate_bstride +
+                                (p.step_ptr ? *p.step_ptr * p.gate_step_stride : 0)
+                          : 0;
+  const bf162 alpha2 = __float2bfloat162_rn(p.alpha);
+  const int bias_mode = p.bias_mode;
+
+  // 8 epilogue warps: each drains one 128-column half; 4 epilogue warps (quantised-B kernel): both halves in turn
+#pragma unroll 1
+  for (int hh = 0; hh < (EPI_WARPS == 4 ? 2 : 1); ++hh) {
+  const int chalf = EPI_WARPS == 4 ? hh : ((warp - 2) >> 2);
+  const uint32_t t_row = t_acc + chalf * 128 + (static_cast<uint32_t>(q * 32) << 16);
+  const int n_half0 = n_t * BLOCK_N + chalf * 128;
+  const bool half_seg1 = (p.n_split > 0) && (n_half0 >= p.n_split);
+  if (QKROPE && p.ev0 == EV_QKROPE && !half_seg1 && n_half0 < p.N) {
+    epi_qkrope(p, t_row, n_half0, grow, valid);
+  } else
+#pragma unroll 1
+  for (int chunk = 0; chunk < 4; ++chunk) {
+    const int n0 = n_t * BLOCK_N + chalf * 128 + chunk * 32;
+    if (n0 >= p.N) break;  // warp-uniform
+    uint32_t acc_r[32];
+    tmem_ld32(t_row + chunk * 32, acc_r);
+    tc_wait_ld();
+    if (!valid) continue;
+    const bool seg1 = (p.n_split > 0) && (n0 >= p.n_split);
+    bf16* outp = seg1 ? p.out1 + grow * p.ld1 + (n0 - p.n_split + p.col_off1) : p.out0 + grow * p.ld0 + n0;
+    const int ev = seg1 ? p.ev1 : p.ev0;
+    const bf16* resp = (ev == EV_RES || ev == EV_GATE_RES) ? p.res + grow * p.ld0 + n0 : nullptr;
+    const bf16* gatep = (ev == EV_GATE_RES) ? p.gate + gate_off + n0 : nullptr;
+    const bf16* biasp = (bias_mode != BIAS_NONE) ? p.bias + n0 : nullptr;
+    if (n0 + 32 <= p.N) {
+      // warp-uniform dispatch to a fully specialised 2 x 16-column body
+#define FB_EPI_CASE(B, E)                                                                  \
+  case (B) * EV_KINDS + (E):                                                               \
+epi16<B, E>(acc_r, outp, biasp, gatep, resp, alpha2);                                  \
+epi16<B, E>(acc_r + 16, outp + 16, biasp ? biasp + 16 : nullptr, gatep ? gatep + 16 : nullptr, \
+            resp ? resp + 16 : nullptr, alpha2);                                       \
+break;
+#define FB_EPI_BIAS(B) \
+  FB_EPI_CASE(B, EV_PLAIN) FB_EPI_CASE(B, EV_GELU) FB_EPI_CASE(B, EV_RES) FB_EPI_CASE(B, EV_GATE_RES) FB_EPI_CASE(B, EV_ALPHA)
+      switch (bias_mode * EV_KINDS + ev) {
+        FB_EPI_BIAS(BIAS_NONE)
+        FB_EPI_BIAS(BIAS_FUSED)
+        FB_EPI_BIAS(BIAS_AFTER_ROUND)
+        default:
+          break;
+      }
+#undef FB_EPI_BIAS
+#undef FB_EPI_CASE
+    } else {
+      epi_slow(acc_r, p.N - n0, outp, biasp, bias_mode, ev, gatep, resp, p.alpha);
+    }
+  }
+  }  // hh
+}
+
 template <bool CTA2, bool QB, bool CL4 = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams P) {
   static_assert(!CL4 || (CTA2 && !QB), "CL4 is a pair-of-pairs build for dense weights");
@@ -723,78 +806,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       TileCoord tc = decode_tile(P, t);
       const GemmProblemDev& p = P.p[tc.prob];
       const int m_t = UNIT_CTAS * tc.m_t + static_cast<int>(rank_cl);
-      const int r = q * 32 + lane;  // row inside the tile == TMEM lane
-      long long grow;
-      bool valid;
-      if (p.conv) {
-        int per_img = p.tiles_h * p.tiles_w;
-        int cn = m_t / per_img;
-        int rem = m_t - cn * per_img;
-        int h = (rem / p.tiles_w) * CONV_TH + r / CONV_TW;
-        int w = (rem % p.tiles_w) * CONV_TW + r % CONV_TW;
-        valid = (m_t < p.tiles_m) && (h < p.cH) && (w < p.cW);
-        grow = (static_cast<long long>(cn) * p.cH + h) * p.cW + w;
-      } else {
-        grow = static_cast<long long>(m_t) * BLOCK_M + r;
-        valid = grow < p.M;
-      }
-      const long long gate_off =
-          (p.gate != nullptr) ? (p.rows_per_batch > 0 ? grow / p.rows_per_batch : 0) * p.gate_bstride +
-                                    (p.step_ptr ? *p.step_ptr * p.gate_step_stride : 0)
-                              : 0;
-      const bf162 alpha2 = __float2bfloat162_rn(p.alpha);
-      const int bias_mode = p.bias_mode;
-
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      // 8 epilogue warps: each drains one 128-column half; 4 epilogue warps (quantised-B kernel): both halves in turn
-#pragma unroll 1
-      for (int hh = 0; hh < (EPI_WARPS == 4 ? 2 : 1); ++hh) {
-      const int chalf = EPI_WARPS == 4 ? hh : ((warp - 2) >> 2);
-      const uint32_t t_row = tmem_base + acc * BLOCK_N + chalf * 128 + (static_cast<uint32_t>(q * 32) << 16);
-      const int n_half0 = tc.n_t * BLOCK_N + chalf * 128;
-      const bool half_seg1 = (p.n_split > 0) && (n_half0 >= p.n_split);
-      if (p.ev0 == EV_QKROPE && !half_seg1 && n_half0 < p.N) {
-        epi_qkrope(p, t_row, n_half0, grow, valid);
-      } else
-#pragma unroll 1
-      for (int chunk = 0; chunk < 4; ++chunk) {
-        const int n0 = tc.n_t * BLOCK_N + chalf * 128 + chunk * 32;
-        if (n0 >= p.N) break;  // warp-uniform
-        uint32_t acc_r[32];
-        tmem_ld32(t_row + chunk * 32, acc_r);
-        tc_wait_ld();
-        if (!valid) continue;
-        const bool seg1 = (p.n_split > 0) && (n0 >= p.n_split);
-        bf16* outp = seg1 ? p.out1 + grow * p.ld1 + (n0 - p.n_split + p.col_off1) : p.out0 + grow * p.ld0 + n0;
-        const int ev = seg1 ? p.ev1 : p.ev0;
-        const bf16* resp = (ev == EV_RES || ev == EV_GATE_RES) ? p.res + grow * p.ld0 + n0 : nullptr;
-        const bf16* gatep = (ev == EV_GATE_RES) ? p.gate + gate_off + n0 : nullptr;
-        const bf16* biasp = (bias_mode != BIAS_NONE) ? p.bias + n0 : nullptr;
-        if (n0 + 32 <= p.N) {
-          // warp-uniform dispatch to a fully specialised 2 x 16-column body
-#define FB_EPI_CASE(B, E)                                                                  \
-  case (B) * EV_KINDS + (E):                                                               \
-    epi16<B, E>(acc_r, outp, biasp, gatep, resp, alpha2);                                  \
-    epi16<B, E>(acc_r + 16, outp + 16, biasp ? biasp + 16 : nullptr, gatep ? gatep + 16 : nullptr, \
-                resp ? resp + 16 : nullptr, alpha2);                                       \
-    break;
-#define FB_EPI_BIAS(B) \
-  FB_EPI_CASE(B, EV_PLAIN) FB_EPI_CASE(B, EV_GELU) FB_EPI_CASE(B, EV_RES) FB_EPI_CASE(B, EV_GATE_RES) FB_EPI_CASE(B, EV_ALPHA)
-          switch (bias_mode * EV_KINDS + ev) {
-            FB_EPI_BIAS(BIAS_NONE)
-            FB_EPI_BIAS(BIAS_FUSED)
-            FB_EPI_BIAS(BIAS_AFTER_ROUND)
-            default:
-              break;
-          }
-#undef FB_EPI_BIAS
-#undef FB_EPI_CASE
-        } else {
-          epi_slow(acc_r, p.N - n0, outp, biasp, bias_mode, ev, gatep, resp, p.alpha);
-        }
-      }
-      }  // hh
+      epi_drain<EPI_WARPS>(p, tc.n_t, m_t, tmem_base + acc * BLOCK_N, warp, lane);
       // release the accumulator back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -814,6 +828,198 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   if (warp == 1) {
     tc_fence_after();
     if (CTA2) tmem_dealloc_2sm(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BIG tiles for the long-K GEMMs (MLP-down K = 12288, single-block linear2 K = 15360).
+//
+// Measured on the 256x256-per-pair kernel above (scripts/gemm_trace.py): the MMA thread waits for TMA data 16-24 % of
+// every tile; an SM has to ingest 32 KB per 512 MMA clocks (64 B/clk) and gets ~51.  This kernel halves the W bytes per
+// FLOP: a CTA pair computes a 512x256 tile as TWO M = 256 MMAs per k-step that share one W tile, i.e. per SM and
+// k-block 2 x 16 KB of A + 16 KB of W for 1024 MMA clocks (48 B/clk).  Both 128x256 fp32 accumulators of the tile fill
+// the CTA's 512 TMEM columns, so the epilogue can no longer hide behind the next tile's main loop; with K >= 8192 the
+// main loop is 200-250 k clocks per tile and the exposed epilogue (a few k clocks, partly overlapped: accumulator 0
+// is released and refilled while accumulator 1 drains) is small against the TMA wait it removes.
+//
+// Wave quantisation: 4608x3072 is 108 such tiles on 74 CTA pairs.  The work list is therefore hybrid: as many FULL
+// waves of 512x256 tiles as fit (positions [0, n_big)), and the remaining positions as their two 256x256 halves
+// ("small" items: one accumulator, alternating so that they double-buffer like the kernel above).  Items are dealt
+// round-robin: for linear2, every pair computes one BIG tile and 68 of the 74 pairs one small tile.
+// Dense weights, no conv mode; any epilogue variant (it reuses epi_drain).
+// ------------------------------------------------------------------------------------------------
+struct BigCfg {
+  static constexpr int STAGES = 4;
+  static constexpr int B_BYTES = (BLOCK_N / 2) * BLOCK_K * 2;     // this CTA's half of the 256 W rows: 16 KB
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + B_BYTES;       // [A sub-tile 0][A sub-tile 1][W half] = 48 KB
+  static constexpr size_t SMEM = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+struct BigItem {
+  int prob, n_t, nsub;  // nsub = 0: nothing to do (second half of an odd M edge)
+  int blk0;             // first 256-row block of the item; sub-tile s covers block blk0 + s
+};
+
+__device__ __forceinline__ BigItem decode_big_item(const GemmParams& P, int w) {
+  int pos, sub_sel = -1;
+  if (w < P.n_big) {
+    pos = w;
+  } else {
+    const int r = w - P.n_big;
+    pos = P.n_big + (r >> 1), sub_sel = r & 1;
+  }
+  const TileCoord tc = decode_tile(P, pos);
+  const GemmProblemDev& p = P.p[tc.prob];
+  const int blocks = (p.tiles_m + 1) / 2;  // 256-row blocks of the problem
+  const bool have2 = 2 * tc.m_t + 1 < blocks;
+  BigItem it;
+  it.prob = tc.prob, it.n_t = tc.n_t;
+  if (sub_sel < 0) {
+    it.blk0 = 2 * tc.m_t, it.nsub = have2 ? 2 : 1;
+  } else {
+    it.blk0 = 2 * tc.m_t + sub_sel, it.nsub = (sub_sel == 0 || have2) ? 1 : 0;
+  }
+  return it;
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_big_kernel(const __grid_constant__ GemmParams P) {
+  constexpr int STAGES = BigCfg::STAGES;
+  constexpr int STAGE_BYTES = BigCfg::STAGE_BYTES;
+  constexpr int EPI_WARPS = 8;
+  const uint32_t cta_rank = cluster_ctarank();
+  const int unit_id = blockIdx.x / 2;
+  const int num_units = gridDim.x / 2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;  // [2] one per accumulator
+  uint64_t* tmem_empty = tmem_full + 2;      // [2]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < P.count; ++i) {
+      tma_prefetch_desc(&P.p[i].tmap_a);
+      tma_prefetch_desc(&P.p[i].tmap_b);
+    }
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 2 * EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2sm(tmem_base_slot, 512);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+  pdl_launch_dependents();
+  pdl_wait();
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t bar_base = mapa_u32(smem_u32(full_bar), 0);  // the leader's barriers collect both CTAs' bytes
+      for (int w = unit_id; w < P.total_items; w += num_units) {
+        const BigItem it = decode_big_item(P, w);
+        if (it.nsub == 0) continue;
+        const GemmProblemDev& p = P.p[it.prob];
+        const int b_row0 = it.n_t * BLOCK_N + static_cast<int>(cta_rank) * (BLOCK_N / 2);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          const uint32_t bar = bar_base + stage * 8;
+          if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (it.nsub * A_BYTES + BigCfg::B_BYTES));
+          for (int s = 0; s < it.nsub; ++s)
+            tma_load_2d_2sm(sa + s * A_BYTES, &p.tmap_a, bar, kb * BLOCK_K,
+                            (2 * (it.blk0 + s) + static_cast<int>(cta_rank)) * BLOCK_M);
+          tma_load_2d_2sm(sa + 2 * A_BYTES, &p.tmap_b, bar, kb * BLOCK_K, b_row0);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (leader CTA) =================
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * BLOCK_M, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t acc_phase = 0;  // bit a: phase of accumulator a
+      int small_count = 0;
+      for (int w = unit_id; w < P.total_items; w += num_units) {
+        const BigItem it = decode_big_item(P, w);
+        if (it.nsub == 0) continue;
+        const GemmProblemDev& p = P.p[it.prob];
+        int acc0 = 0;
+        if (it.nsub == 2) small_count = 0; else acc0 = small_count++ & 1;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait_cluster(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint64_t db = umma_smem_desc_sw128(sa + 2 * A_BYTES, 16, 1024);
+          for (int s = 0; s < it.nsub; ++s) {
+            const int acc = acc0 + s;
+            if (kb == 0) {  // the epilogue (of both CTAs) must have drained this accumulator
+              mbar_wait_cluster(&tmem_empty[acc], ((acc_phase >> acc) & 1u) ^ 1u);
+              tc_fence_after();
+            }
+            const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+            const uint64_t da = umma_smem_desc_sw128(sa + s * A_BYTES, 16, 1024);
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / 16; ++k) umma_ss_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            if (kb == p.num_kb - 1) {  // this accumulator is complete once the MMAs issued so far retire
+              tc_commit_2sm(&tmem_full[acc], 3);
+              acc_phase ^= 1u << acc;
+            }
+          }
+          tc_commit_2sm(&empty_bar[stage], 3);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else {
+    // ================= epilogue warps =================
+    uint32_t ephase = 0;  // bit a: phase of accumulator a
+    int small_count = 0;
+    for (int w = unit_id; w < P.total_items; w += num_units) {
+      const BigItem it = decode_big_item(P, w);
+      if (it.nsub == 0) continue;
+      const GemmProblemDev& p = P.p[it.prob];
+      int acc0 = 0;
+      if (it.nsub == 2) small_count = 0; else acc0 = small_count++ & 1;
+      for (int s = 0; s < it.nsub; ++s) {
+        const int acc = acc0 + s;
+        const int m_t = 2 * (it.blk0 + s) + static_cast<int>(cta_rank);
+        mbar_wait(&tmem_full[acc], (ephase >> acc) & 1u);
+        tc_fence_after();
+        epi_drain<EPI_WARPS, false>(p, it.n_t, m_t, tmem_base + acc * BLOCK_N, warp, lane);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
+        ephase ^= 1u << acc;
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 512);
   }
 }
 
@@ -839,6 +1045,8 @@ int gemm_init_device() {
                                        static_cast<int>(GemmCfg<true, true>::SMEM)));
     FB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(GemmCfg<true>::SMEM)));
+    FB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(BigCfg::SMEM)));
     attr_once.done();
   }
   return 0;
@@ -880,6 +1088,20 @@ int launch_gemm(const GemmDesc* descs, int count, cudaStream_t stream) {
     max_clusters4 = n;
   }
   if (use_cl4 && max_clusters4 < 1) use_cl4 = false;
+  // BIG tiles (512x256 per pair, see gemm_tcgen05_big_kernel): dense long-K problems with at least one full wave
+  // ("gemm_big" = 1: K >= 8192; 2: every eligible GEMM, for experiments)
+  const int big_flag = get_flag("gemm_big");
+  bool use_big = use_pair && !quant_b && !use_cl4 && big_flag > 0;
+  {
+    long long positions = 0;
+    for (int i = 0; i < count && use_big; ++i) {
+      const GemmDesc& d = descs[i];
+      if (d.conv || d.qkrope || d.K % BLOCK_K != 0 || (big_flag < 2 && d.K < 8192)) use_big = false;
+      const int blocks = (d.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+      positions += static_cast<long long>((blocks + 1) / 2) * ((d.N + BLOCK_N - 1) / BLOCK_N);
+    }
+    if (positions < num_sms() / 2) use_big = false;
+  }
   const int b_box_rows = use_pair ? GemmCfg<true>::B_ROWS : GemmCfg<false>::B_ROWS;
   GemmParams P;
   memset(&P, 0, sizeof(P));
@@ -966,7 +1188,7 @@ int launch_gemm(const GemmDesc* descs, int count, cudaStream_t stream) {
       }
     }
     p.tiles_n = (d.N + BLOCK_N - 1) / BLOCK_N;
-    p.sched_m = use_cl4 ? (p.tiles_m + 3) / 4 : (use_pair ? (p.tiles_m + 1) / 2 : p.tiles_m);
+    p.sched_m = (use_cl4 || use_big) ? (p.tiles_m + 3) / 4 : (use_pair ? (p.tiles_m + 1) / 2 : p.tiles_m);
     // L2-aware rasterisation: when the whole A operand fits comfortably in the 126 MB L2 (activations of one DiT
     // block: 28 MB), walk all of M for a few N tiles at a time so that every weight panel is fetched from HBM once
     // (ncu: 650 MB -> ~algorithmic 360 MB of DRAM traffic for the 4608x21504x3072 launch); otherwise groups of 8.
@@ -1016,6 +1238,11 @@ int launch_gemm(const GemmDesc* descs, int count, cudaStream_t stream) {
   }
   P.total_tiles = tile;
   P.trace = g_gemm_trace;
+  if (use_big) {
+    const int units = num_sms() / 2;
+    P.n_big = (tile / units) * units;  // full waves of 512x256 tiles; the rest as 256x256 halves
+    P.total_items = P.n_big + 2 * (tile - P.n_big);
+  }
   double flops = 0, bytes = 0;
   for (int i = 0; i < count; ++i) {
     flops += 2.0 * descs[i].M * static_cast<double>(descs[i].N) * descs[i].K;
@@ -1025,7 +1252,10 @@ int launch_gemm(const GemmDesc* descs, int count, cudaStream_t stream) {
   ProfScope _ps(KK_GEMM, flops, bytes, stream);
   count_launch(KK_GEMM);
   const bool pdl = get_flag("pdl") != 0;
-  if (use_cl4) {
+  if (use_big) {
+    FB_CHECK_CUDA(launch_ex(gemm_tcgen05_big_kernel, dim3(2 * std::min(P.total_items, num_sms() / 2)), dim3(GEMM_THREADS),
+                            BigCfg::SMEM, stream, 2, pdl, P));
+  } else if (use_cl4) {
     FB_CHECK_CUDA(launch_ex(gemm_tcgen05_kernel<true, false, true>, dim3(4 * std::min(tile, max_clusters4)),
                             dim3(GEMM_THREADS), GemmCfg<true>::SMEM, stream, 4, pdl, P));
   } else if (use_pair) {

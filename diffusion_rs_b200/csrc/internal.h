@@ -161,6 +161,7 @@ int get_flag(const char* name);
 int launch_gemm(const GemmDesc* descs, int count, cudaStream_t stream);
 int gemm_init_device();       // per-device kernel attributes; also called lazily by launch_gemm
 int attention_init_device();  // same for launch_attention
+int attention_num_variants();
 int set_gemm_trace(long long* buf);  // debug: device buffer of 64*4 int64 written by scheduling unit 0, or nullptr
 
 // ---- tcgen05 flash attention: q,k,v [B,H,L,128] bf16 -> out rows [B, L, H*128] split at L_split ----

@@ -27,7 +27,9 @@ SIGNATURES = {
                                 c_int, c_int, c_void_p, c_int64, c_int, c_void_p, c_float, c_void_p]),
     "fluxb200_linear_quant": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int64,
                                       c_int, c_int, c_int, c_int, c_int, c_void_p]),
-    "fluxb200_sdpa": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p]),
+    "fluxb200_sdpa": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float,
+                              c_void_p]),
+    "fluxb200_attn_variants": (c_int, []),
     "fluxb200_debug_sdpa_trace": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p,
                                           c_void_p]),
     "fluxb200_debug_gemm_trace": (c_int, [c_void_p]),

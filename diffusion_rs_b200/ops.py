@@ -58,15 +58,15 @@ def linear_quant(x, packed, aux, kind: str, N: int, bias=None, *, blocksize=64, 
     return out
 
 
-def sdpa(q, k, v, scale: float):
-    """q,k,v [B,H,L,128] -> [B,L,H*128] — ops::sdpa (ops.rs:247-262) + transpose/flatten (model.rs:101)."""
+def sdpa(q, k, v, scale: float, softcapping: float = 1.0):
+    """q,k,v [B,H,L,128] -> [B,L,H*128] — ops::sdpa(q, k, v, scale, softcapping) (ops.rs:247-262) followed by the
+    transpose(1,2).flatten_from(2) of its FLUX call site (model.rs:101).  head_dim != 128 or softcapping != 1.0 are
+    rejected by the library (a Rust shim falls through to the stock ops::sdpa on that status)."""
     _chk_bf16(q, k, v)
     B, H, Lq, D = q.shape
-    if D != 128:
-        raise L.Fluxb200Error("sdpa: head_dim must be 128")
     out = torch.empty(B, Lq, H * D, device=q.device, dtype=torch.bfloat16)
-    L.check(L.load().fluxb200_sdpa(L.ptr(q), L.ptr(k), L.ptr(v), L.ptr(out), B, H, Lq, float(scale),
-                                   L.current_stream()))
+    L.check(L.load().fluxb200_sdpa(L.ptr(q), L.ptr(k), L.ptr(v), L.ptr(out), B, H, Lq, D, float(scale),
+                                   float(softcapping), L.current_stream()))
     return out
 
 

@@ -55,10 +55,16 @@ int fluxb200_linear_quant(const void* a, int64_t lda, const void* packed, const 
                           int32_t blocksize, const void* bias, void* out, int64_t ldo, int32_t M, int32_t N, int32_t K,
                           int32_t bias_mode, int32_t act, fluxb200_stream_t stream);
 
-/* Joint attention. q,k,v: bf16 [B,H,L,128]; out: bf16 [B,L,H*128] (== transpose(1,2).flatten_from(2)).
- * Replaces diffusion_rs_backend::ops::sdpa (ops.rs:247-262) + the casts in model.rs:40-51, softcapping = 1. */
+/* Joint attention.  q,k,v: bf16 [B,H,L,head_dim] contiguous (the (bs, qhead, seq, hidden) operands of
+ * diffusion_rs_backend::ops::sdpa, ops.rs:247-262, with k/v heads == q heads); out: bf16 [B,L,H*head_dim], i.e. the
+ * reference's (bs, qhead, seq, v_hidden) result ALREADY passed through `.transpose(1,2).flatten_from(2)`, which is what
+ * its only FLUX call site does next (model.rs:97-102) - a shim that needs the untransposed tensor transposes back.
+ * Preconditions, checked: head_dim == 128, softcapping == 1.0 (off).  Anything else returns non-zero with a message
+ * and enqueues nothing, so that the caller can fall through to the stock ops::sdpa. */
 int fluxb200_sdpa(const void* q, const void* k, const void* v, void* out, int32_t B, int32_t H, int32_t L,
-                  float scale, fluxb200_stream_t stream);
+                  int32_t head_dim, float scale, float softcapping, fluxb200_stream_t stream);
+/* Number of run-time selectable builds of the attention kernel ("attn_variant" flag values 0 .. n-1). */
+int fluxb200_attn_variants(void);
 
 /* Debug/profiling twin of fluxb200_sdpa: additionally records clock64 stamps of CTA 0's pipeline stages into `trace`
  * (device buffer of 64*2*8 int64: [kv block][query tile][stage]); used by scripts/attn_trace.py only. */

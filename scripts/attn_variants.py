@@ -13,7 +13,7 @@ from diffusion_rs_b200 import build, lib as L, ops  # noqa: E402
 build.build()
 lib = L.load()
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
-variants = [int(a) for a in sys.argv[1:]] or list(range(10))
+variants = [int(a) for a in sys.argv[1:]] or list(range(lib.fluxb200_attn_variants()))
 
 
 def timeit(fn, iters=12, warm=3):

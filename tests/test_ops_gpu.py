@@ -42,6 +42,36 @@ def test_linear_plain(fluxlib, M, N, K):
     assert mism < 0.02, mism
 
 
+@pytest.mark.parametrize("M,N,K,flag", [(4608, 3072, 12288, 1), (4112, 3072, 8192, 1), (4608, 3072, 15360, 1),
+                                        (2500, 12288, 3072, 2)])
+def test_linear_big_tiles_bit_identical(fluxlib, M, N, K, flag):
+    """The 512x256-per-CTA-pair kernel for the long-K GEMMs (hybrid work list: full waves of big tiles + 256x256 halves)
+    accumulates every output element over k in the same order as the 256x256 kernel: same bits, including the fused
+    gate * x + residual epilogue and ragged / odd M edges (4112 rows = 33 tiles of 128)."""
+    from diffusion_rs_b200 import lib as L
+    from diffusion_rs_b200 import ops
+    x = _rand((M, K), 11)
+    w = _rand((N, K), 12, 1.0 / math.sqrt(K))
+    b = _rand((N,), 13, 0.02)
+    gate = _rand((2, N), 14, 0.5)
+    res = _rand((M, N), 15)
+    rpb = (M + 1) // 2
+    outs = []
+    for f in (0, flag):
+        L.check(fluxlib.fluxb200_set_flag(b"gemm_big", f))
+        if flag == 2:
+            outs.append(ops.linear(x, w, b, bias_mode=ops.BIAS_FUSED, act=ops.ACT_GELU))
+        else:
+            outs.append(ops.linear(x, w, b, bias_mode=ops.BIAS_FUSED, gate=gate, rows_per_batch=rpb, res=res))
+    L.check(fluxlib.fluxb200_set_flag(b"gemm_big", 1))
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1])
+    if flag == 1 and M == 4112:  # and the result is right, not just equal
+        b_idx = (torch.arange(M, device="cuda") // rpb)
+        ref = O.rb(res.float() + O.rb(gate.float()[b_idx] * O.linear(x.float(), w.float(), b.float(), fused_bias=True)))
+        assert _err(outs[1], ref)[1] < 2e-3
+
+
 def test_linear_bias_after_round_and_nobias(fluxlib):
     from diffusion_rs_b200 import ops
     M, N, K = 256, 512, 256
@@ -92,6 +122,20 @@ def test_linear_gate_residual(fluxlib):
     ref2 = O.rb(res.float() + O.rb(gate.float()[:, None, :] * pre_gpu))
     mism = (out.float() != ref2).float().mean().item()
     assert mism < 1e-3, mism
+
+
+def test_sdpa_rejects_what_the_flash_kernel_does_not_cover(fluxlib):
+    """ops::sdpa(q, k, v, scale, softcapping) (ops.rs:247-262): head_dim != 128 or softcapping != 1.0 must fail loudly
+    (status + message, nothing enqueued) so that a shim falls through to the stock path instead of computing garbage."""
+    from diffusion_rs_b200 import lib as L
+    from diffusion_rs_b200 import ops
+    q = torch.randn(1, 2, 64, 128, device="cuda").bfloat16()
+    with pytest.raises(L.Fluxb200Error, match="softcapping"):
+        ops.sdpa(q, q, q, 0.1, softcapping=30.0)
+    q64 = torch.randn(1, 2, 64, 64, device="cuda").bfloat16()
+    with pytest.raises(L.Fluxb200Error, match="head_dim"):
+        ops.sdpa(q64, q64, q64, 0.1)
+    assert ops.sdpa(q, q, q, 0.1).shape == (1, 64, 256)
 
 
 @pytest.mark.parametrize("B,H,L", [(1, 2, 256), (1, 3, 512), (2, 2, 384), (1, 2, 1000), (1, 24, 4608)])

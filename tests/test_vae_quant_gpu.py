@@ -81,8 +81,34 @@ def test_vae_decode_vs_oracle(fluxlib, B, h, w):
     tru = OV.VaeOracle(cfg, W, O.F32).decode(z.float())
     e1, e2, e3 = _rel(out, ref), _rel(out, tru), _rel(ref, tru)
     print(f"\nVAE decode B={B} {h}x{w}: |ours-ref|={e1:.3e} |ours-f32|={e2:.3e} |ref-f32|={e3:.3e}")
-    assert e1 < 3e-2
-    assert e2 < 1.5 * e3 + 1e-3
+    assert e1 < 1.5e-2
+    assert e2 < 1.2 * e3 + 1e-3
+
+
+@pytest.mark.slow
+def test_vae_decode_1024_vs_oracle(fluxlib):
+    """The size the benchmark runs: 128x128 latents -> 1024x1024 pixels (AutoEncoderKl::decode, vae.rs:437-455;
+    [1,128,1024,1024] activations, 1 M-pixel implicit-GEMM conv tiles, 16384-token mid-block attention)."""
+    from diffusion_rs_b200.vae import AutoEncoderKl, VaeConfig
+    cfg = OV.VaeConfig()
+    W = OV.make_weights(cfg)
+    vae = AutoEncoderKl.new(VaeConfig(), {k: v.cuda() for k, v in W.items()})
+    z = torch.randn(1, 16, 128, 128, generator=torch.Generator().manual_seed(19)).bfloat16()
+    out = vae.decode(z.cuda())
+    torch.cuda.synchronize()
+    got = out.float().cpu()
+    del out, vae
+    ref = OV.VaeOracle(cfg, W, O.REF).decode(z.float())
+    e1 = _rel(got, ref)
+    print(f"\nVAE decode 1024x1024: |ours-ref|={e1:.3e}")
+    assert torch.isfinite(got).all() and got.shape == (1, 3, 1024, 1024)
+    assert e1 < 1.5e-2
+    # the u8 image the pipeline returns (clamp, (x+1)*127.5 in bf16, truncation): off-by-one levels only
+    def u8(x):
+        return O.rb(O.rb(x.clamp(-1, 1) + 1.0) * 127.5).to(torch.uint8).int()
+    d = (u8(O.rb(got)) - u8(ref)).abs()
+    print(f"u8 image: mean abs diff {d.float().mean():.3f} levels, max {d.max().item()}")
+    assert d.float().mean().item() < 1.0
 
 
 def test_vae_packed_u8(fluxlib):
@@ -213,9 +239,11 @@ def _quantize_model_weights(weights, kind):
     return tensors, deq
 
 
-@pytest.mark.parametrize("kind", ["nf4", "fp4", "int8", "q4k"])
-def test_quantised_dit_step(fluxlib, kind):
-    """C3 / C5 semantics at reduced depth: oracle weight = dequant(quant(W)); bnb adds the bias after rounding."""
+@pytest.mark.parametrize("kind,geom", [("nf4", (8, 8, 64)), ("fp4", (8, 8, 64)), ("int8", (8, 8, 64)), ("q4k", (8, 8, 64)),
+                                       ("nf4", (64, 64, 512)), ("q4k", (64, 64, 512))])
+def test_quantised_dit_step(fluxlib, kind, geom):
+    """C3 / C5 semantics at reduced depth (1 + 1 blocks), small and at the headline width L = 4096 + 512: oracle
+    weight = dequant(quant(W)); bnb adds the bias after rounding."""
     from diffusion_rs_b200.transformer import DT_Q4K, FluxConfig, FluxTransformer
     cfg = OF.FluxConfig(num_layers=1, num_single_layers=1, guidance_embeds=True)
     weights = OF.make_weights(cfg)
@@ -227,7 +255,8 @@ def test_quantised_dit_step(fluxlib, kind):
         else:
             m.load_weight(name, t.cuda())
     m.finalize()
-    B, h2, w2, l_txt = 1, 8, 8, 64
+    B = 1
+    h2, w2, l_txt = geom
     g = torch.Generator().manual_seed(11)
     img = torch.randn(B, h2 * w2, 64, generator=g).bfloat16()
     txt = torch.randn(B, l_txt, 4096, generator=g).bfloat16()
@@ -259,8 +288,8 @@ def test_quantised_dit_step(fluxlib, kind):
 
     ref = QOracle(cfg, deq, O.REF).forward(img.float(), ids, txt.float(), t, y.float(), gd)
     e = _rel(out, ref)
-    print(f"\n{kind} DiT step: rel err {e:.3e}")
-    assert e < 3e-2
+    print(f"\n{kind} DiT step L={h2 * w2 + l_txt}: rel err {e:.3e}")
+    assert e < 1e-2
 
 
 @pytest.mark.parametrize("kind", ["nf4", "fp4", "q4k", "int8"])
