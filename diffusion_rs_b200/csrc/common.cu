@@ -79,7 +79,7 @@ ProfScope::~ProfScope() {
 }
 
 static int g_flag_qkrope = 1, g_flag_pair = -1, g_flag_fdq = 0, g_flag_attn = -1, g_flag_pdl = -1, g_flag_cl4 = -1,
-           g_flag_graph = -1, g_flag_big = -1;
+           g_flag_graph = -1, g_flag_big = -1, g_flag_dqo = -1;
 int get_flag(const char* name) {
   if (!strcmp(name, "qkrope_fusion")) return g_flag_qkrope;
   if (!strcmp(name, "fused_dequant")) return g_flag_fdq;
@@ -96,6 +96,13 @@ int get_flag(const char* name) {
       g_flag_graph = (e && e[0] == '0') ? 0 : 1;
     }
     return g_flag_graph;
+  }
+  if (!strcmp(name, "dequant_overlap")) {
+    if (g_flag_dqo < 0) {
+      const char* e = getenv("FLUXB200_DEQUANT_OVERLAP");
+      g_flag_dqo = (e && e[0] == '0') ? 0 : 1;
+    }
+    return g_flag_dqo;
   }
   if (!strcmp(name, "gemm_big")) {
     if (g_flag_big < 0) {
@@ -240,6 +247,7 @@ int fluxb200_set_flag(const char* name, int value) {
   if (!strcmp(name, "gemm_cl4")) { fb::g_flag_cl4 = value ? 1 : 0; return 0; }
   if (!strcmp(name, "step_graph")) { fb::g_flag_graph = value ? 1 : 0; return 0; }
   if (!strcmp(name, "gemm_big")) { fb::g_flag_big = value; return 0; }
+  if (!strcmp(name, "dequant_overlap")) { fb::g_flag_dqo = value ? 1 : 0; return 0; }
   return fb::fail(std::string("set_flag: unknown flag ") + name);
 }
 void fluxb200_profile_enable(int on) {

@@ -159,6 +159,13 @@ struct fluxb200_model {
   long long mod_row_elems = 0;
   bf16* wscratch[2] = {nullptr, nullptr};  // dequantised-weight staging, double-buffered (quantised models only)
   int wscratch_cur = 0;
+  // Expansion pipeline of the staged quantised path: the quantised Linears of one step in the order the step uses
+  // them; the expansion of weight j+1 runs on a side stream while the GEMM that consumes weight j occupies the tensor
+  // cores (the expansion is HBM-bound, the GEMM is not: they co-reside on the SMs)
+  std::vector<const FusedLinear*> worder;
+  size_t wnext = 0, wissued = 0;
+  cudaStream_t side_stream = nullptr, cap_side_stream = nullptr;
+  cudaEvent_t ev_fork[4] = {nullptr, nullptr, nullptr, nullptr}, ev_ready[2] = {nullptr, nullptr};
   size_t wscratch_elems = 0;
   bool any_quant = false;
   // step graph (denoise): captured on a private stream, replayed on the caller's
@@ -362,6 +369,8 @@ static bool fused_dequant_ok(const FusedLinear& fl) {
   return true;
 }
 
+static int expand_into(const FusedLinear& fl, bf16* stage, cudaStream_t st);
+
 // Weight operand for the GEMM: dense pointer, or expand the quantised members into a staging buffer (ONE launch for
 // all members of the fused linear).  The two staging buffers alternate so that the expansion of the next layer never
 // has to wait for the GEMM that is still reading the previous one.
@@ -376,10 +385,16 @@ static int weight_operand(fluxb200_model* m, const FusedLinear& fl, const bf16**
   }
   bf16* stage = m->wscratch[m->wscratch_cur];
   m->wscratch_cur ^= 1;
+  if (int rc = expand_into(fl, stage, st)) return rc;
+  *w = stage;
+  return 0;
+}
+
+static int expand_into(const FusedLinear& fl, bf16* stage, cudaStream_t st) {
   DequantBatch batch;
   batch.count = 0;
   for (auto& mb : fl.members) {
-    FB_REQUIRE(batch.count < DequantBatch::MAX, "weight_operand: too many fused members");
+    FB_REQUIRE(batch.count < DequantBatch::MAX, "expand_into: too many fused members");
     DequantJob& j = batch.job[batch.count++];
     j.packed = mb.packed, j.absmax = mb.absmax, j.scb = mb.scb;
     j.out = stage + static_cast<size_t>(mb.row_off) * fl.K;
@@ -387,8 +402,37 @@ static int weight_operand(fluxb200_model* m, const FusedLinear& fl, const bf16**
     j.col = fl.K, j.blocksize = mb.blocksize;
     j.kind = mb.q == Q_NF4 ? QB_NF4 : (mb.q == Q_FP4 ? QB_FP4 : (mb.q == Q_Q4K ? QB_Q4K : QB_INT8));
   }
-  if (int rc = launch_dequant_batch(batch, st)) return rc;
-  *w = stage;
+  return launch_dequant_batch(batch, st);
+}
+
+// ---- expansion pipeline (see fluxb200_model::worder) ----
+static bool pipe_enabled(const fluxb200_model* m) {
+  return m->any_quant && !m->worder.empty() && get_flag("dequant_overlap") != 0 && get_flag("fused_dequant") == 0 &&
+         !profiling_enabled();
+}
+static void pipe_begin(fluxb200_model* m) { m->wnext = m->wissued = 0; }
+// enqueue the expansion of worder[j] on `side`, ordered after everything launched on `main` so far (in particular
+// after the GEMM that last read this staging buffer)
+static int pipe_issue(fluxb200_model* m, size_t j, cudaStream_t main, cudaStream_t side) {
+  cudaEvent_t fork = m->ev_fork[j & 3], ready = m->ev_ready[j & 1];
+  FB_CHECK_CUDA(cudaEventRecord(fork, main));
+  FB_CHECK_CUDA(cudaStreamWaitEvent(side, fork, 0));
+  if (int rc = expand_into(*m->worder[j], m->wscratch[j & 1], side)) return rc;
+  FB_CHECK_CUDA(cudaEventRecord(ready, side));
+  m->wissued = j + 1;
+  return 0;
+}
+// weight operand of `fl` for the next GEMM on `main`; also starts the expansion of the step's following weight
+static int pipe_acquire(fluxb200_model* m, const FusedLinear& fl, const bf16** w, cudaStream_t main, cudaStream_t side) {
+  const size_t j = m->wnext;
+  FB_REQUIRE(j < m->worder.size() && m->worder[j] == &fl, "internal: quantised weight requested out of order");
+  if (m->wissued <= j)
+    if (int rc = pipe_issue(m, j, main, side)) return rc;
+  FB_CHECK_CUDA(cudaStreamWaitEvent(main, m->ev_ready[j & 1], 0));
+  *w = m->wscratch[j & 1];
+  if (j + 1 < m->worder.size())
+    if (int rc = pipe_issue(m, j + 1, main, side)) return rc;
+  m->wnext = j + 1;
   return 0;
 }
 
@@ -489,6 +533,8 @@ int fluxb200_dequantize_q4k_bf16(const void* blocks, void* out, int64_t n, fluxb
                             static_cast<cudaStream_t>(stream));
 }
 
+void fluxb200_model_destroy(fluxb200_model* m);
+
 int fluxb200_model_create(const fluxb200_flux_config* cfg, fluxb200_model** out) {
   FB_REQUIRE(cfg && out, "model_create: null argument");
   FB_REQUIRE(cfg->num_attention_heads * HEAD_DIM == D, "num_attention_heads * 128 must equal HIDDEN_SIZE 3072");
@@ -506,9 +552,13 @@ int fluxb200_model_create(const fluxb200_flux_config* cfg, fluxb200_model** out)
   auto* m = new fluxb200_model();
   m->cfg = *cfg;
   cudaError_t e = cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->cap_side_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->side_stream, cudaStreamNonBlocking);
+  for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&m->ev_fork[i], cudaEventDisableTiming);
+  for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&m->ev_ready[i], cudaEventDisableTiming);
   if (e != cudaSuccess) {
-    delete m;
-    return fail(std::string("model_create: cudaStreamCreate failed: ") + cudaGetErrorString(e));
+    fluxb200_model_destroy(m);
+    return fail(std::string("model_create: stream / event creation failed: ") + cudaGetErrorString(e));
   }
   *out = m;
   return 0;
@@ -521,6 +571,12 @@ void fluxb200_model_destroy(fluxb200_model* m) {
   for (auto& g : m->graphs)
     if (g.exec) cudaGraphExecDestroy(g.exec);
   if (m->cap_stream) cudaStreamDestroy(m->cap_stream);
+  if (m->cap_side_stream) cudaStreamDestroy(m->cap_side_stream);
+  if (m->side_stream) cudaStreamDestroy(m->side_stream);
+  for (auto ev : m->ev_fork)
+    if (ev) cudaEventDestroy(ev);
+  for (auto ev : m->ev_ready)
+    if (ev) cudaEventDestroy(ev);
   for (int i = 0; i < 2; ++i)
     if (m->wscratch[i]) cudaFree(m->wscratch[i]);
   delete m;
@@ -644,6 +700,18 @@ int fluxb200_model_finalize(fluxb200_model* m, fluxb200_stream_t stream) {
   if (m->any_quant) {
     for (int i = 0; i < 2; ++i) FB_CHECK_CUDA(cudaMalloc(&m->wscratch[i], m->wscratch_elems * 2));
   }
+  // the quantised Linears of one step, in the order step_core consumes them (pipe_acquire checks it)
+  m->worder.clear();
+  auto use = [&](const FusedLinear& fl) {
+    if (fl.quant) m->worder.push_back(&fl);
+  };
+  use(m->img_in);
+  for (auto& b : m->dbl) {
+    use(b.img_qkv), use(b.txt_qkv), use(b.img_proj), use(b.txt_proj);
+    use(b.img_mlp1), use(b.txt_mlp1), use(b.img_mlp2), use(b.txt_mlp2);
+  }
+  for (auto& b : m->sgl) use(b.lin1), use(b.lin2);
+  use(m->final_proj);
   m->finalized = true;
   return 0;
 #undef TRY
@@ -755,8 +823,15 @@ static int compute_modulations(fluxb200_model* m, const Workspace& w, const floa
 //                         img += bf16(pred * dt) (pipelines/sampling.rs:43) is the final projection's epilogue, in place
 //                         on `lat` (out = res + gate * val with gate = dt_tab[step], two roundings)
 static int step_core(fluxb200_model* m, const Workspace& w, const bf16* img_in, bf16* pred_out, bf16* lat,
-                     const int* step_ptr, int B, int l_img, int l_txt, cudaStream_t st) {
+                     const int* step_ptr, int B, int l_img, int l_txt, cudaStream_t st, cudaStream_t side) {
   const auto& c = m->cfg;
+  // quantised weights: staged expansion, software-pipelined one weight ahead on the side stream (or in-order on `st`)
+  const bool piped = pipe_enabled(m);
+  pipe_begin(m);
+  auto W = [&](const FusedLinear& fl, const bf16** wp) -> int {
+    if (piped && fl.quant) return pipe_acquire(m, fl, wp, st, side);
+    return weight_operand(m, fl, wp, st);
+  };
   const int L = l_img + l_txt;
   const int Mi = B * l_img, Mt = B * l_txt, Mx = B * L;
   const int H = c.num_attention_heads;
@@ -780,7 +855,7 @@ static int step_core(fluxb200_model* m, const Workspace& w, const bf16* img_in, 
   // ---- img_in (model.rs:812); txt_in(txt) was hoisted ----
   {
     const bf16* wi = nullptr;
-    TRY(weight_operand(m, m->img_in, &wi, st));
+    TRY(W(m->img_in, &wi));
     GemmDesc d = gemm_for(m->img_in, wi, img_in, Mi, w.img, D);
     TRY(launch_gemm(&d, 1, st));
   }
@@ -808,7 +883,7 @@ static int step_core(fluxb200_model* m, const Workspace& w, const bf16* img_in, 
         FusedLinear& f = s == 0 ? fi : ft;
         GemmDesc& g = s == 0 ? gi : gt;
         const bf16* wq = nullptr;
-        if (int r = weight_operand(m, f, &wq, st)) return r;
+        if (int r = W(f, &wq)) return r;
         g.w = wq;
         g.qb = (f.quant && wq == nullptr) ? &f.qb : nullptr;
         if (int r = launch_gemm(&g, 1, st)) return r;
@@ -877,7 +952,7 @@ static int step_core(fluxb200_model* m, const Workspace& w, const bf16* img_in, 
     TRY(ln_mod(w.x, L, 0, L, j, 0, 1, w.xm));
     {
       const bf16* w1 = nullptr;
-      TRY(weight_operand(m, b.lin1, &w1, st));
+      TRY(W(b.lin1, &w1));
       GemmDesc g = gemm_for(b.lin1, w1, w.xm, Mx, w.qkv, 3 * D);
       g.n_split = 3 * D;  // q|k|v -> qkv buffer; proj_mlp -> gelu -> [attn | mlp] buffer at column D
       g.out1 = w.big, g.ld1 = CAT, g.col_off1 = D, g.act1 = ACT_GELU;
@@ -894,7 +969,7 @@ static int step_core(fluxb200_model* m, const Workspace& w, const bf16* img_in, 
     }
     {
       const bf16* w2 = nullptr;
-      TRY(weight_operand(m, b.lin2, &w2, st));
+      TRY(W(b.lin2, &w2));
       GemmDesc g = gemm_for(b.lin2, w2, w.big, Mx, w.x, D);
       gated(g, j, 2, L, w.x);
       TRY(launch_gemm(&g, 1, st));
@@ -905,7 +980,7 @@ static int step_core(fluxb200_model* m, const Workspace& w, const bf16* img_in, 
     const int jf = 2 * c.num_layers + c.num_single_layers;
     TRY(ln_mod(w.x, L, l_txt, l_img, jf, 1, 0, w.xm));
     const bf16* wf = nullptr;
-    TRY(weight_operand(m, m->final_proj, &wf, st));
+    TRY(W(m->final_proj, &wf));
     GemmDesc g = gemm_for(m->final_proj, wf, w.xm, Mi, step_ptr ? lat : pred_out, c.in_channels);
     if (step_ptr) {  // fused Euler update
       g.gate = w.dt_tab, g.gate_bstride = 0, g.rows_per_batch = l_img, g.res = lat;
@@ -913,6 +988,7 @@ static int step_core(fluxb200_model* m, const Workspace& w, const bf16* img_in, 
     }
     TRY(launch_gemm(&g, 1, st));
   }
+  if (piped) FB_REQUIRE(m->wnext == m->worder.size() && m->wissued == m->wnext, "internal: expansion pipeline out of step");
   return 0;
 }
 
@@ -937,6 +1013,7 @@ static unsigned flags_signature() {
   s = s * 2 + (get_flag("fused_dequant") & 1);
   s = s * 2 + (get_flag("gemm_pair") & 1);
   s = s * 2 + (get_flag("gemm_cl4") & 1);
+  s = s * 2 + (get_flag("dequant_overlap") & 1);
   s = s * 16 + (get_flag("gemm_big") & 15);
   s = s * 64 + (get_flag("attn_variant") & 63);
   return s;
@@ -965,7 +1042,7 @@ static StepGraph* step_graph_for(fluxb200_model* m, const Workspace& w, void* ws
     cudaGetLastError();
     return nullptr;
   }
-  int rc = step_core(m, w, w.lat, nullptr, w.lat, w.step, B, l_img, l_txt, m->cap_stream);
+  int rc = step_core(m, w, w.lat, nullptr, w.lat, w.step, B, l_img, l_txt, m->cap_stream, m->cap_side_stream);
   if (rc == 0) rc = launch_step_advance(w.step, m->cap_stream);
   cudaGraph_t graph = nullptr;
   e = cudaStreamEndCapture(m->cap_stream, &graph);
@@ -1013,7 +1090,7 @@ int fluxb200_model_forward(fluxb200_model* m, const void* img, const void* img_i
                                    io.y, batch, batch, st))
     return rc;
   if (int rc = step_core(m, w, static_cast<const bf16*>(img), static_cast<bf16*>(out), nullptr, nullptr, batch, l_img,
-                         l_txt, st))
+                         l_txt, st, m->side_stream))
     return rc;
   m->last_B = batch, m->last_limg = l_img, m->last_ltxt = l_txt, m->last_ws = w;
   return 0;
@@ -1070,7 +1147,7 @@ int fluxb200_model_denoise(fluxb200_model* m, void* img, const void* img_ids, co
     m->last_used_graph = 1;
   } else {
     for (int s = 0; s < steps; ++s) {
-      if (int rc = step_core(m, w, w.lat, nullptr, w.lat, w.step, batch, l_img, l_txt, st)) return rc;
+      if (int rc = step_core(m, w, w.lat, nullptr, w.lat, w.step, batch, l_img, l_txt, st, m->side_stream)) return rc;
       if (int rc = launch_step_advance(w.step, st)) return rc;
     }
   }

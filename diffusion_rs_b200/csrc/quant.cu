@@ -182,7 +182,9 @@ __device__ __forceinline__ void q4k_scale_min(const uint8_t* sc, int is, float d
   m = __fmul_rn(dmin, static_cast<float>(mm));
 }
 
-__global__ void __launch_bounds__(256) dequant_batch_kernel(const DequantBatch batch) {
+// <= 40 registers so that a block co-resides with the persistent GEMM CTA of its SM (320 threads x 168 registers): the
+// expansion of the NEXT weight runs on a side stream while the tensor cores work on the current one
+__global__ void __launch_bounds__(256, 6) dequant_batch_kernel(const DequantBatch batch) {
   __shared__ float2 lut2[256];
   const DequantJob& j = batch.job[blockIdx.y];
   if (j.kind == QB_NF4 || j.kind == QB_FP4) {

@@ -300,6 +300,8 @@ int fluxb200_clip_forward(fluxb200_clip* m, const int32_t* ids, void* hidden_out
  *   "attn_variant"   build of the attention kernel, see attention.cu (default 0; FLUXB200_ATTN_VARIANT=n)
  *   "pdl"            programmatic dependent launch for GEMM / attention / LN-modulate (default 1; FLUXB200_PDL=0)
  *   "step_graph"     fluxb200_model_denoise replays one captured CUDA graph per step (default 1; FLUXB200_STEP_GRAPH=0)
+ *   "dequant_overlap" staged quantised path: the expansion of the next weight runs on a side stream under the current
+ *                    GEMM (default 1; FLUXB200_DEQUANT_OVERLAP=0)
  *   "gemm_big"       512x256-per-CTA-pair tiles for the long-K GEMMs (default 1; FLUXB200_GEMM_BIG=0)
  * FLUXB200_GEMM_MAX_UNITS=n limits the pair GEMM to n CTA pairs (experiments only). */
 int fluxb200_set_flag(const char* name, int value);

@@ -1,4 +1,5 @@
-import json, sys
+import json, signal, sys
+signal.signal(signal.SIGPIPE, signal.SIG_DFL)  # `| head` must not produce BrokenPipe noise
 j = json.load(open(sys.argv[1]))
 for k in ('value', 'ms_per_step', 'dit_ms_per_step', 'frac_of_dense_gemm_roofline', 'gpu_launches', 'clocks', 'profiled_image_ms'):
     print(k, j.get(k))
