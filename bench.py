@@ -114,59 +114,98 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port (CPU restatement of the reference) timed on host cores
 # ----------------------------------------------------------------------------------------------------------------------
-def cpu_reference_sample(repeats: int = 1) -> dict:
-    """One double-stream + one single-stream block at full width (L = 4096 + 512), f32 math on bf16-rounded tensors,
-    all host cores; extrapolated x19 / x38 x 50 steps (+ VAE by FLOPs) to images/s.  ~10-30 s of CPU work."""
-    import torch
-    from oracle import flux as OF
-    from oracle import ops as O
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    cfg = OF.FluxConfig(num_layers=1, num_single_layers=1, guidance_embeds=True)
-    w = OF.make_weights(cfg)
-    orc = OF.FluxOracle(cfg, w, O.REF)
-    l_img, l_txt = (HEIGHT // 16) * (WIDTH // 16), L_TXT
-    g = torch.Generator().manual_seed(1234)
-    img = O.rb(torch.randn(1, l_img, D, generator=g))
-    txt = O.rb(torch.randn(1, l_txt, D, generator=g))
-    vec = O.rb(torch.randn(1, D, generator=g))
-    pe = OF.embed_nd(OF.make_ids(HEIGHT // 16, WIDTH // 16, l_txt), O.REF)
-    best_d = best_s = float("inf")
-    for _ in range(max(1, repeats)):
+def workload_config(height, width, num_steps, batch, world, quant, double_layers=19, single_layers=38) -> dict:
+    """The `config` object of the JSON line - shared by both arms so that the driver compares like with like."""
+    l_img = ((height + 15) // 16) * ((width + 15) // 16)
+    return {"workload": f"FLUX.1-dev {height}x{width} {num_steps}-step bf16 batch={batch} per GPU "
+                        f"(1 step = 1 image = {num_steps} DiT steps + VAE decode)",
+            "l_img": l_img, "l_txt": L_TXT, "guidance": GUIDANCE, "weights": "random-init " + (quant or "bf16"),
+            "parallelism": f"dp{world} (prompt sharding, NCCL weight broadcast at load only)",
+            "l2": "inputs+weights per step (24 GB) >> 126 MB L2; no explicit flush needed",
+            "double_layers": double_layers, "single_layers": single_layers}
+
+
+class CpuReference:
+    """The reference's CPU path for this workload, restated (oracle port: torch CPU = oneDNN/AVX-512, f32 math on
+    bf16-rounded tensors - the reference's own CPU backend cannot multiply bf16), on all host cores.
+    One SAMPLE = one DoubleStreamBlock + one SingleStreamBlock at the full width of the workload (L = l_img + 512):
+    2 of the 57 x num_steps blocks of an image, ~3 s on 16 cores.  images/s = sample's share of an image's FLOPs /
+    sample time (every block of a kind costs the same; the VAE share is extrapolated by FLOPs)."""
+
+    def __init__(self, height=HEIGHT, width=WIDTH, num_steps=NUM_STEPS):
+        import torch
+        from oracle import flux as OF
+        from oracle import ops as O
+        self.torch = torch
+        self.cores = os.cpu_count() or 1
+        torch.set_num_threads(self.cores)
+        cfg = OF.FluxConfig(num_layers=1, num_single_layers=1, guidance_embeds=True)
+        self.orc = OF.FluxOracle(cfg, OF.make_weights(cfg), O.REF)
+        h2, w2 = (height + 15) // 16, (width + 15) // 16
+        self.l_img, self.l_txt, self.num_steps = h2 * w2, L_TXT, num_steps
+        g = torch.Generator().manual_seed(1234)
+        self.img = O.rb(torch.randn(1, self.l_img, D, generator=g))
+        self.txt = O.rb(torch.randn(1, self.l_txt, D, generator=g))
+        self.vec = O.rb(torch.randn(1, D, generator=g))
+        self.pe = OF.embed_nd(OF.make_ids(h2, w2, self.l_txt), O.REF)
+        L = self.l_img + self.l_txt
+        f_block = 24 * L * D * D + 4 * L * L * D
+        f_image = num_steps * 57 * f_block + F_VAE_1024 * (self.l_img / 4096.0)
+        self.fraction = 2 * f_block / f_image
+
+    def sample(self) -> tuple[float, float, float]:
+        """-> (seconds, double-block seconds, single-block seconds)"""
         t0 = time.perf_counter()
-        i2, t2 = orc.double_block(0, img, txt, vec, pe)
+        i2, t2 = self.orc.double_block(0, self.img, self.txt, self.vec, self.pe)
         t1 = time.perf_counter()
-        x = orc.single_block(0, torch.cat([t2, i2], 1), vec, pe)
+        self.orc.single_block(0, self.torch.cat([t2, i2], 1), self.vec, self.pe)
         t2_ = time.perf_counter()
-        best_d, best_s = min(best_d, t1 - t0), min(best_s, t2_ - t1)
-    step_s = 19 * best_d + 38 * best_s
-    f_step = dit_step_flops(l_img, l_txt)
-    vae_s = step_s * F_VAE_1024 / f_step
-    img_s = NUM_STEPS * step_s + vae_s
-    return dict(value=1.0 / img_s, unit=UNIT, cores=cores, kind="port",
-                sample=(f"oracle port (torch CPU f32 on bf16-rounded tensors): 1 double block {best_d:.2f}s + 1 single "
-                        f"block {best_s:.2f}s at L=4608, extrapolated x19/x38 x{NUM_STEPS} steps + VAE by FLOPs"),
-                seconds_per_image=img_s, double_block_s=best_d, single_block_s=best_s)
+        return t2_ - t0, t1 - t0, t2_ - t1
+
+    def describe(self, n, secs, d, s) -> dict:
+        value = n * self.fraction / secs
+        return dict(value=value, unit=UNIT, cores=self.cores, kind="port",
+                    sample=(f"oracle port (torch CPU f32 on bf16-rounded tensors, {self.cores} threads): {n} sample(s) of 1 double "
+                            f"block ({d:.2f}s) + 1 single block ({s:.2f}s) at L={self.l_img + self.l_txt} = "
+                            f"{self.fraction:.3e} of an image's FLOPs each; images/s = share / time"),
+                    seconds_per_image=1.0 / value)
+
+
+def cpu_reference_sample(height=HEIGHT, width=WIDTH, num_steps=NUM_STEPS) -> dict:
+    """cpu_baseline leg of our arm: one sample (~3 s) plus ~10 s of weight generation."""
+    ref = CpuReference(height, width, num_steps)
+    ref.sample()  # warm-up: oneDNN primitive creation
+    secs, d, s = ref.sample()
+    return ref.describe(1, secs, d, s)
 
 
 def run_reference(args):
+    """`--impl reference`: W untimed samples, then exactly K timed samples (one "step" = one bounded sample of the
+    workload, see CpuReference); rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     t0 = time.perf_counter()
-    for _ in range(args.warmup if args.warmup < 2 else 1):
-        cpu_reference_sample(1)
-    samples = [cpu_reference_sample(1) for _ in range(max(1, min(args.steps, 3)))]
-    best = max(samples, key=lambda s: s["value"])
+    ref = CpuReference(args.height, args.width, args.num_steps)
+    for _ in range(max(1, args.warmup)):
+        ref.sample()
+    secs = d = s = 0.0
+    for _ in range(args.steps):
+        a, b, c = ref.sample()
+        secs, d, s = secs + a, d + b, s + c
+    desc = ref.describe(args.steps, secs, d / args.steps, s / args.steps)
     line = {
-        "impl": "reference", "metric": METRIC, "value": best["value"], "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": best["seconds_per_image"] * 1e3,
+        "impl": "reference", "metric": METRIC, "value": desc["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 math on bf16-rounded tensors",
         "data": "synthetic",
-        "config": {"workload": "FLUX.1-dev 1024x1024 50-step batch=1 (reference CPU path, oracle port; the Rust "
-                               "reference cannot be built here: no cargo/rustc)", "l_img": 4096, "l_txt": L_TXT},
-        "cpu_baseline": {k: best[k] for k in ("value", "unit", "cores", "kind", "sample")},
-        "e2e": {"value": best["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": dict(workload_config(args.height, args.width, args.num_steps, args.batch, args.gpus, args.quant),
+                       reference_arm="CPU path restated (oracle port); the Rust reference cannot be built here (no "
+                                     "cargo/rustc).  One step = one bounded sample, value = sample share of an image / time",
+                       sample_fraction_of_image=ref.fraction),
+        "cpu_baseline": {k: desc[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": desc["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "seconds_per_image_extrapolated": desc["seconds_per_image"],
         "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
     }
     print(json.dumps(line))
@@ -336,24 +375,37 @@ def run_ours(args):
             traffic = json.loads(tj.read_text()).get("dram_bytes_per_launch")
         roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel", "achieved": ach,
                     "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tflops_sustained"],
-                    "traffic": traffic, "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step)",
+                    "traffic": traffic,
+                    "traffic_source": ("ncu --set full capture of the 4608x21504x3072 launch committed under profiles/ "
+                                       "(dram bytes read + written per launch), not measured in this run"),
+                    "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step)",
                     "launches": gemm["launches"], "avg_launch_ms": gemm["ms"] / gemm["launches"],
                     "share_of_step": gemm["ms"] / ms_prof}
-    cpu = cpu_reference_sample(1) if (world == 1 and not args.no_cpu_baseline) else None
+    # the other kernel classes against their own roofline (attention: tensor; the rest: HBM, algorithmic bytes)
+    rooflines = {}
+    for kind, v in kinds.items():
+        if not v.get("launches") or kind == "gemm_tcgen05":
+            continue
+        if v["flops"] > 0:
+            a = v["flops"] / (v["ms"] / 1e3) / 1e12
+            rooflines[kind] = {"bound": "tensor", "achieved": a, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
+                               "frac": a / pk["tflops_sustained"], "share_of_step": v["ms"] / ms_prof}
+        elif v["bytes"] > 0:
+            a = v["bytes"] / (v["ms"] / 1e3) / 1e9
+            rooflines[kind] = {"bound": "hbm", "achieved": a, "peak": pk["hbm"], "unit": "GB/s", "frac": a / pk["hbm"],
+                               "share_of_step": v["ms"] / ms_prof}
+    cpu = (cpu_reference_sample(args.height, args.width, args.num_steps)
+           if (world == 1 and not args.no_cpu_baseline) else None)
     h2d, d2h = pipe.io_bytes(B, params)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if quant is None else f"bf16 (weights {quant})", "data": "synthetic",
-        "config": {"workload": f"FLUX.1-dev {params.height}x{params.width} {params.num_steps}-step bf16 batch={B} per GPU "
-                               f"(1 step = 1 image = {params.num_steps} DiT steps + VAE decode)",
-                   "l_img": l_img, "l_txt": l_txt, "guidance": GUIDANCE, "weights": "random-init " + (quant or "bf16"),
-                   "parallelism": f"dp{world} (prompt sharding, NCCL weight broadcast at load only)",
-                   "l2": "inputs+weights per step (24 GB) >> 126 MB L2; no explicit flush needed",
-                   "double_layers": pipe.transformer.cfg.num_layers, "single_layers": pipe.transformer.cfg.num_single_layers},
+        "config": workload_config(params.height, params.width, params.num_steps, B, world, quant,
+                                  pipe.transformer.cfg.num_layers, pipe.transformer.cfg.num_single_layers),
         "dit_ms_per_step": None, "images_per_s_per_gpu": value / world,
         "frac_of_dense_gemm_roofline": (value / world) * f_img / (pk["tflops_sustained"] * 1e12),
-        "roofline": roofline, "kernels": kinds, "cpu_baseline": ({k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        "roofline": roofline, "rooflines_other": rooflines, "kernels": kinds, "cpu_baseline": ({k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
                                                                  if cpu else None),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps},
@@ -361,6 +413,10 @@ def run_ours(args):
     }
     line["dit_ms_per_step"] = (ms_total / args.steps) / params.num_steps  # upper bound: includes the VAE share
     line["profiled_image_ms"] = ms_prof
+    if clocks and clocks.get("power_w"):  # the loop is power-capped: energy per image is what kernel variants trade
+        line["joules_per_image_per_gpu"] = clocks["power_w"] * (ms_total / args.steps / 1e3) / B
+    graph_used, graph_note = pipe.transformer.denoise_info()
+    line["step_graph"] = {"used": graph_used, "note": graph_note}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -20,14 +20,22 @@ __device__ __forceinline__ float silu_steps(float v) {  // core/op.rs:703-705, b
 }
 
 // ------------------------------------------------------------------------------------------------
-// GroupNorm statistics, two passes like the reference (mean, then centred sum of squares), f32 partials per block,
-// f64 atomics across blocks.  x: [N, HW, C] bf16; stats: double [N, groups, 2] = {sum, centred sumsq}.
-// Thread t owns the 8-channel vector (t % (C/8)); rows of pixels are strided over the block.
+// GroupNorm(32 groups) + optional SiLU on NHWC: ONE statistics pass + one apply pass (the reference runs two
+// statistics passes in f32: mean, then the centred sum of squares; nn/group_norm.rs:39-74).
+// The single pass accumulates SHIFTED moments  S1 = sum(x - c), S2 = sum((x - c)^2)  with the pilot c = the group's
+// first value of the image (so the sums are of O(sigma) terms and  var = (S2 - S1^2/n)/n  has no cancellation
+// problem), f32 per thread (<= 256 terms), f64 across threads / blocks (the result does not depend on the unordered
+// atomic arrival order beyond f64 rounding).  mean and sqrt(var + eps) then agree with the reference's two-pass f32
+// values to ~1e-7 relative, far below the bf16 rounding of the normalised value.
+// x: [N, HW, C] bf16; stats: double [N, groups, 2] = {S1, S2}.  Thread t owns the 8-channel vector t % (C/8).
 // ------------------------------------------------------------------------------------------------
-template <int PASS>
+__device__ __forceinline__ float gn_pilot(const bf16* __restrict__ x, int n, int HW, int C, int cpg, int g) {
+  return __bfloat162float(x[static_cast<long long>(n) * HW * C + g * cpg]);
+}
+
 __global__ void __launch_bounds__(256) gn_stats_kernel(const bf16* __restrict__ x, double* __restrict__ stats, int HW,
                                                        int C, int groups, int pix_per_block) {
-  __shared__ double part[64];  // f64 partials: the result does not depend on the (unordered) atomic arrival order
+  __shared__ double part[64];  // [group][S1, S2]
   const int n = blockIdx.y;
   const int cv = C / 8;                 // vectors per pixel
   const int rows = blockDim.x / cv;     // pixels processed per iteration
@@ -36,73 +44,99 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const bf16* __restrict__ 
   const int cpg = C / groups;
   if (threadIdx.x < 64) part[threadIdx.x] = 0.0;
   __syncthreads();
-  float mean0 = 0.f, mean1 = 0.f;
   const int g0 = (vec * 8) / cpg;
   const int g1 = (vec * 8 + 4) / cpg;  // differs from g0 only when cpg == 4
-  const double cnt = static_cast<double>(HW) * cpg;
-  if (PASS == 1) {
-    mean0 = static_cast<float>(stats[(n * groups + g0) * 2] / cnt);
-    mean1 = static_cast<float>(stats[(n * groups + g1) * 2] / cnt);
-  }
-  float a0 = 0.f, a1 = 0.f;
+  const float c0 = gn_pilot(x, n, HW, C, cpg, g0), c1 = gn_pilot(x, n, HW, C, cpg, g1);
+  float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
   const int p_begin = blockIdx.x * pix_per_block;
   const int p_end = min(HW, p_begin + pix_per_block);
   if (prow < rows) {
-    for (int p = p_begin + prow; p < p_end; p += rows) {
-      float f[8];
-      unpack8v(*reinterpret_cast<const uint4*>(x + (static_cast<long long>(n) * HW + p) * C + vec * 8), f);
-      if (PASS == 0) {
-        a0 += (f[0] + f[1]) + (f[2] + f[3]);
-        a1 += (f[4] + f[5]) + (f[6] + f[7]);
-      } else {
+    const bf16* base = x + static_cast<long long>(n) * HW * C + vec * 8;
+    int p = p_begin + prow;
+    // four independent 16-byte loads in flight per thread
+    for (; p + 3 * rows < p_end; p += 4 * rows) {
+      uint4 u[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) u[k] = *reinterpret_cast<const uint4*>(base + static_cast<long long>(p + k * rows) * C);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float f[8];
+        unpack8v(u[k], f);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float d0 = f[e] - mean0, d1 = f[4 + e] - mean1;
-          a0 += d0 * d0;
-          a1 += d1 * d1;
+          const float d0 = f[e] - c0, d1 = f[4 + e] - c1;
+          s0 += d0, q0 = fmaf(d0, d0, q0);
+          s1 += d1, q1 = fmaf(d1, d1, q1);
         }
       }
     }
+    for (; p < p_end; p += rows) {
+      float f[8];
+      unpack8v(*reinterpret_cast<const uint4*>(base + static_cast<long long>(p) * C), f);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float d0 = f[e] - c0, d1 = f[4 + e] - c1;
+        s0 += d0, q0 = fmaf(d0, d0, q0);
+        s1 += d1, q1 = fmaf(d1, d1, q1);
+      }
+    }
   }
-  atomicAdd(&part[g0], static_cast<double>(a0));
-  atomicAdd(&part[g1], static_cast<double>(a1));
+  if (g0 == g1) {
+    atomicAdd(&part[g0 * 2], static_cast<double>(s0) + static_cast<double>(s1));
+    atomicAdd(&part[g0 * 2 + 1], static_cast<double>(q0) + static_cast<double>(q1));
+  } else {
+    atomicAdd(&part[g0 * 2], static_cast<double>(s0));
+    atomicAdd(&part[g0 * 2 + 1], static_cast<double>(q0));
+    atomicAdd(&part[g1 * 2], static_cast<double>(s1));
+    atomicAdd(&part[g1 * 2 + 1], static_cast<double>(q1));
+  }
   __syncthreads();
-  if (threadIdx.x < groups) {
+  if (threadIdx.x < 2 * groups) {
     const double v = part[threadIdx.x];
-    if (v != 0.0) atomicAdd(&stats[(n * groups + threadIdx.x) * 2 + PASS], v);
+    if (v != 0.0) atomicAdd(&stats[static_cast<long long>(n) * groups * 2 + threadIdx.x], v);
   }
 }
 
-// y = silu?( bf16( bf16( bf16((x - mean) / sqrt(var + eps)) * w ) + b ) )
+// y = silu?( bf16( bf16( bf16((x - mean) / sqrt(var + eps)) * w ) + b ) ); grid = (vector blocks per image, N)
 __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ x, const double* __restrict__ stats,
                                                        const bf16* __restrict__ w, const bf16* __restrict__ b,
                                                        bf16* __restrict__ y, int HW, int C, int groups, float eps,
-                                                       int apply_silu, long long total_vec) {
+                                                       int apply_silu, long long vec_per_image) {
+  __shared__ float2 gs[32];  // per group: mean, sqrt(var + eps)
+  const int n = blockIdx.y;
+  const int cpg = C / groups;
+  if (threadIdx.x < groups) {
+    const int g = threadIdx.x;
+    const double cnt = static_cast<double>(HW) * cpg;
+    const double S1 = stats[(static_cast<long long>(n) * groups + g) * 2];
+    const double S2 = stats[(static_cast<long long>(n) * groups + g) * 2 + 1];
+    const double dm = S1 / cnt;
+    const double var = fmax((S2 - S1 * dm) / cnt, 0.0);
+    const float mean = static_cast<float>(static_cast<double>(gn_pilot(x, n, HW, C, cpg, g)) + dm);
+    gs[g] = make_float2(mean, sqrtf(static_cast<float>(var) + eps));
+  }
+  __syncthreads();
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  if (i >= total_vec) return;
+  if (i >= vec_per_image) return;
   const int cv = C / 8;
   const int vec = static_cast<int>(i % cv);
-  const long long pix = i / cv;
-  const int n = static_cast<int>(pix / HW);
-  const int cpg = C / groups;
-  const double cnt = static_cast<double>(HW) * cpg;
+  const long long off = (static_cast<long long>(n) * vec_per_image + i) * 8;
   float f[8], wf[8], bfv[8], o[8];
-  unpack8v(*reinterpret_cast<const uint4*>(x + i * 8), f);
+  unpack8v(*reinterpret_cast<const uint4*>(x + off), f);
   unpack8v(*reinterpret_cast<const uint4*>(w + vec * 8), wf);
   unpack8v(*reinterpret_cast<const uint4*>(b + vec * 8), bfv);
+  const float2 st0 = gs[(vec * 8) / cpg], st1 = gs[(vec * 8 + 4) / cpg];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
-    const int g = (vec * 8 + e) / cpg;
-    const float mean = static_cast<float>(stats[(n * groups + g) * 2] / cnt);
-    const float var = static_cast<float>(stats[(n * groups + g) * 2 + 1] / cnt);
-    const float nx = rbf((f[e] - mean) / sqrtf(var + eps));
+    const float2 st = e < 4 ? st0 : st1;
+    const float nx = rbf((f[e] - st.x) / st.y);
     float v = rbf(rbf(nx * wf[e]) + bfv[e]);
     if (apply_silu) v = silu_steps(v);
     o[e] = v;
   }
   uint4 u;
   u.x = pack_bf16(o[0], o[1]), u.y = pack_bf16(o[2], o[3]), u.z = pack_bf16(o[4], o[5]), u.w = pack_bf16(o[6], o[7]);
-  *reinterpret_cast<uint4*>(y + i * 8) = u;
+  *reinterpret_cast<uint4*>(y + off) = u;
 }
 
 int launch_groupnorm_silu(const bf16* x, const bf16* w, const bf16* b, bf16* y, int N, int HW, int C, int groups,
@@ -111,14 +145,13 @@ int launch_groupnorm_silu(const bf16* x, const bf16* w, const bf16* b, bf16* y, 
              "groupnorm: needs 32 groups, >= 4 channels per group and C/8 dividing 256");
   FB_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * N * groups * 2, stream));
   const int pix_per_block = 1024;
-  ProfScope _ps(KK_GROUPNORM, 0, 8.0 * N * HW * C, stream);
-  count_launch(KK_GROUPNORM, 3);
+  ProfScope _ps(KK_GROUPNORM, 0, 6.0 * N * HW * C, stream);  // algorithmic: x read twice (stats, apply), y written once
+  count_launch(KK_GROUPNORM, 2);
   dim3 grid((HW + pix_per_block - 1) / pix_per_block, N);
-  gn_stats_kernel<0><<<grid, 256, 0, stream>>>(x, stats, HW, C, groups, pix_per_block);
-  gn_stats_kernel<1><<<grid, 256, 0, stream>>>(x, stats, HW, C, groups, pix_per_block);
-  const long long total_vec = static_cast<long long>(N) * HW * (C / 8);
-  gn_apply_kernel<<<static_cast<unsigned>((total_vec + 255) / 256), 256, 0, stream>>>(x, stats, w, b, y, HW, C, groups,
-                                                                                      eps, apply_silu, total_vec);
+  gn_stats_kernel<<<grid, 256, 0, stream>>>(x, stats, HW, C, groups, pix_per_block);
+  const long long vec_per_image = static_cast<long long>(HW) * (C / 8);
+  gn_apply_kernel<<<dim3(static_cast<unsigned>((vec_per_image + 255) / 256), N), 256, 0, stream>>>(
+      x, stats, w, b, y, HW, C, groups, eps, apply_silu, vec_per_image);
   FB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -235,3 +235,51 @@ def test_tokenizers_mirror_the_reference_construction():
     from diffusion_rs_b200 import lib as L
     with pytest.raises(L.Fluxb200Error):
         pipe.tokenize("a cat")
+
+
+@pytest.mark.gpu
+def test_two_devices_driven_from_two_threads(fluxlib):
+    """SURVEY §8(b) threading row: handles are re-entrant per (device, stream); per-device kernel attributes (opt-in
+    shared memory) are set on every device the process uses, not once per process.  Two models on two GPUs, driven
+    concurrently from two host threads, each equal to its own single-threaded result."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs in one process")
+    import threading
+    from diffusion_rs_b200.transformer import FluxConfig, FluxTransformer
+    from oracle import flux as OF
+    cfg = OF.FluxConfig(num_layers=1, num_single_layers=1, guidance_embeds=True)
+    weights = OF.make_weights(cfg)
+    B, h2, w2, l_txt = 1, 12, 12, 64
+    g = torch.Generator().manual_seed(5)
+    img = torch.randn(B, h2 * w2, 64, generator=g).bfloat16()
+    txt = torch.randn(B, l_txt, 4096, generator=g).bfloat16()
+    y = torch.randn(B, 768, generator=g).bfloat16()
+    ids = OF.make_ids(h2, w2, l_txt).bfloat16()
+    ts = OF.get_timesteps(3, OF.calculate_shift(16))
+
+    def run(dev, out, reps):
+        torch.cuda.set_device(dev)
+        d = f"cuda:{dev}"
+        m = FluxTransformer.new(FluxConfig(num_layers=1, num_single_layers=1, guidance_embeds=True),
+                                {k: v.to(d) for k, v in weights.items()})
+        with torch.cuda.stream(torch.cuda.Stream(device=d)):
+            for _ in range(reps):
+                x = img.to(d).clone()
+                m.denoise(x, ids[l_txt:][None].contiguous().to(d), txt.to(d), ids[:l_txt][None].contiguous().to(d),
+                          y.to(d), 3.5, ts)
+            torch.cuda.current_stream().synchronize()
+        out[dev] = x.cpu()
+
+    solo, both = {}, {}
+    for dev in (0, 1):
+        run(dev, solo, 1)
+    threads = [threading.Thread(target=run, args=(dev, both, 3)) for dev in (0, 1)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    torch.cuda.set_device(0)
+    assert set(both) == {0, 1}, "a worker thread failed"
+    for dev in (0, 1):
+        assert torch.equal(solo[dev], both[dev])
+    assert torch.equal(solo[0], solo[1])
