@@ -156,14 +156,15 @@ struct AttnCfg {
   static constexpr size_t SMEM = XCH_OFF + 2 * 2 * 2 * 128 * sizeof(float);
 };
 
-template <bool PAIR, int POLY_MASK, int NHAND, bool PP, int RPT, bool TRACE>
-__global__ void __launch_bounds__((8 * RPT + 4) * 32, 1) attention_tcgen05_kernel(const __grid_constant__ AttnParams P) {
+template <bool PAIR, int POLY_MASK, int NHAND, bool PP, int RPT, bool TRACE, bool COOP = false>
+__global__ void __launch_bounds__((COOP ? 12 : 8 * RPT + 4) * 32, 1) attention_tcgen05_kernel(const __grid_constant__ AttnParams P) {
   static_assert(RPT == 1 || (RPT == 2 && NHAND == 1), "two threads per row hand P over in one piece");
-  constexpr int NSW = 4 * RPT;        // softmax warps per tile
-  constexpr int W_TMA = 2 * NSW;      // first control warp
+  static_assert(!COOP || RPT == 2, "COOP: the 8 softmax warps split every row of both tiles in two");
+  constexpr int NSW = 4 * RPT;                   // softmax warps that serve one tile (arrivals per p_ready barrier)
+  constexpr int W_TMA = COOP ? NSW : 2 * NSW;    // first control warp = number of softmax warps
   constexpr int W_MMA = W_TMA + 1;
   constexpr int COLS = 128 / RPT;     // score columns per softmax thread
-  constexpr int SM_THREADS = 2 * NSW * 32;
+  constexpr int SM_THREADS = W_TMA * 32;
   using Cfg = AttnCfg<PAIR>;
   constexpr int ST = Cfg::ST;
   constexpr int KVB = Cfg::KV_BYTES;
@@ -237,8 +238,8 @@ __global__ void __launch_bounds__((8 * RPT + 4) * 32, 1) attention_tcgen05_kerne
   // control warpgroup hands part of its share to the softmax warpgroups, which keep their score columns in registers
   // (120 + 2 x 192 = 3 x 168;  64 + 4 x 104 = 5 x 96).
   if (warp >= W_TMA) {
-    if (RPT == 1) asm volatile("setmaxnreg.dec.sync.aligned.u32 120;");
-    else          asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+    if (RPT == 1 || COOP) asm volatile("setmaxnreg.dec.sync.aligned.u32 120;");
+    else                  asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
     if (warp == W_TMA) {
       if (lane == 0) {
         // ---------------- TMA producer (PAIR: one per CTA; bytes are credited to the leader's barriers) ----------------
@@ -373,138 +374,155 @@ __global__ void __launch_bounds__((8 * RPT + 4) * 32, 1) attention_tcgen05_kerne
       }
     }
   } else {
-    if (RPT == 1) asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
-    else          asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
-    // ---------------- softmax / correction / epilogue: thread = (row r of tile g, column slice h) ----------------
-    const int g = warp / NSW;            // query tile
-    const int h = (warp % NSW) >> 2;     // which COLS-wide slice of the row (always 0 when RPT == 1)
+    if (RPT == 1 || COOP) asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
+    else                  asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    // ---------------- softmax / correction / epilogue: thread = (row r, column slice h) of tile g ----------------
+    // COOP: the same 8 warps serve BOTH query tiles, kv block by kv block (tile 0, then tile 1): while a tile waits for
+    // its P.V + next Q.K^T on the tensor core, all warps work on the other tile, so the softmax part of a tile's
+    // dependency chain is half as long (64 instead of 128 columns per thread) at the same total work per warp.
+    constexpr int NT = COOP ? 2 : 1;     // tiles served by this warp
+    const int g_first = COOP ? 0 : warp / NSW;
+    const int h = COOP ? (warp >> 2) : ((warp % NSW) >> 2);  // which COLS-wide slice of the row (0 when RPT == 1)
     const int q = warp & 3;              // TMEM lane quarter
     const int r = q * 32 + lane;         // row in tile
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
-    const uint32_t tS = TM_S + g * 128 + h * COLS + lane_off;        // my score columns
-    const uint32_t tP = TM_S + g * 128 + h * (COLS / 2) + lane_off;  // my P values, bf16 pairs
-    const uint32_t tO = TM_O + g * 128 + h * COLS + lane_off;        // my O columns
     const float sl2 = P.sl2;
-    float m_run = -INFINITY;  // running (possibly stale) row max of raw scores
-    float l_run = 0.f;        // row sum over my columns
+    float m_run[NT], l_run[NT];  // running (possibly stale) row max of raw scores; row sum over my columns
+#pragma unroll
+    for (int t = 0; t < NT; ++t) m_run[t] = -INFINITY, l_run[t] = 0.f;
     long long* const tr = (TRACE && trace && r == 0 && h == 0) ? trace : nullptr;
-    const uint32_t pbar0 = PAIR ? mapa_u32(smem_u32(&p_ready[g]), 0) : smem_u32(&p_ready[g]);  // + 16 B per instalment
-    auto arrive_p = [&](int hnd) {
-      if (PAIR) mbar_arrive_cluster_relaxed(pbar0 + hnd * 16);
-      else      mbar_arrive(&p_ready[hnd * 2 + g]);
-    };
-    // RPT == 2: exchange slots with the thread that holds the other half of this row
-    const uint32_t x_mine = smem_u32(smem + Cfg::XCH_OFF) + ((g * 2 + h) * 128 + r) * 4;
-    const uint32_t x_other = smem_u32(smem + Cfg::XCH_OFF) + ((g * 2 + (1 - h)) * 128 + r) * 4;
-    const uint32_t xbar = 3 + g * 4 + q;  // named barrier shared by warps w and w+4 of the tile
     // The two tiles' softmax warps share the SM's MUFU unit.  A ping-pong pair of named barriers lets only one tile
     // be in its exp2 phase at a time, which keeps the tiles in anti-phase: while tile g exponentiates, the tensor
-    // core runs the other tile's P.V and next Q.K^T.
-    if (PP && g == 1) named_bar_arrive(1, SM_THREADS);  // tile 0 goes first
+    // core runs the other tile's P.V and next Q.K^T.  (COOP: the tiles alternate by construction.)
+    if (PP && !COOP && g_first == 1) named_bar_arrive(1, SM_THREADS);  // tile 0 goes first
 
     for (int j = 0; j < P.nkv; ++j) {
-      mbar_wait(&s_full[g], j & 1);
-      tc_fence_after();
-      if (TRACE && tr && j < 64) tr[(j * 2 + g) * 8 + 0] = clock64();
-      uint32_t s[COLS];
 #pragma unroll
-      for (int c = 0; c < COLS / 32; ++c) tmem_ld32(tS + c * 32, &s[c * 32]);
-      tc_wait_ld();
-      if (TRACE && tr && j < 64) tr[(j * 2 + g) * 8 + 1] = clock64();
-      const int kv_valid = P.L - j * TKV - h * COLS;  // valid columns among mine; >= COLS except on the last block
-      if (kv_valid < COLS) {
+      for (int t = 0; t < NT; ++t) {
+        const int g = g_first + t;
+        const uint32_t tS = TM_S + g * 128 + h * COLS + lane_off;        // my score columns
+        const uint32_t tP = TM_S + g * 128 + h * (COLS / 2) + lane_off;  // my P values, bf16 pairs
+        const uint32_t tO = TM_O + g * 128 + h * COLS + lane_off;        // my O columns
+        const uint32_t pbar0 = PAIR ? mapa_u32(smem_u32(&p_ready[g]), 0) : smem_u32(&p_ready[g]);  // + 16 B per instalment
+        auto arrive_p = [&](int hnd) {
+          if (PAIR) mbar_arrive_cluster_relaxed(pbar0 + hnd * 16);
+          else      mbar_arrive(&p_ready[hnd * 2 + g]);
+        };
+        // RPT == 2: exchange slots with the thread that holds the other half of this row
+        const uint32_t x_mine = smem_u32(smem + Cfg::XCH_OFF) + ((g * 2 + h) * 128 + r) * 4;
+        const uint32_t x_other = smem_u32(smem + Cfg::XCH_OFF) + ((g * 2 + (1 - h)) * 128 + r) * 4;
+        const uint32_t xbar = 3 + g * 4 + q;  // named barrier shared by the two warps that split this row quarter
+
+        mbar_wait(&s_full[g], j & 1);
+        tc_fence_after();
+        if (TRACE && tr && j < 64) tr[(j * 2 + g) * 8 + 0] = clock64();
+        uint32_t s[COLS];
 #pragma unroll
-        for (int i = 0; i < COLS; ++i)
-          if (i >= kv_valid) s[i] = __float_as_uint(-INFINITY);
-      }
-      // row max over my columns: four independent 3-input max chains
-      float bm0 = -INFINITY, bm1 = -INFINITY, bm2 = -INFINITY, bm3 = -INFINITY;
+        for (int c = 0; c < COLS / 32; ++c) tmem_ld32(tS + c * 32, &s[c * 32]);
+        tc_wait_ld();
+        if (TRACE && tr && j < 64) tr[(j * 2 + g) * 8 + 1] = clock64();
+        const int kv_valid = P.L - j * TKV - h * COLS;  // valid columns among mine; >= COLS except on the last block
+        if (kv_valid < COLS) {
 #pragma unroll
-      for (int i = 0; i < COLS; i += 8) {
-        bm0 = fmax3(bm0, __uint_as_float(s[i + 0]), __uint_as_float(s[i + 1]));
-        bm1 = fmax3(bm1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
-        bm2 = fmax3(bm2, __uint_as_float(s[i + 4]), __uint_as_float(s[i + 5]));
-        bm3 = fmax3(bm3, __uint_as_float(s[i + 6]), __uint_as_float(s[i + 7]));
-      }
-      float bmax = fmaxf(fmaxf(bm0, bm1), fmaxf(bm2, bm3));
-      if (RPT == 2) {  // both threads of the row must use the same reference
-        const uint32_t xo = (j & 1) * 2048;
-        st_shared_f32(x_mine + xo, bmax);
-        named_bar_sync(xbar, 64);
-        bmax = fmaxf(bmax, ld_shared_f32(x_other + xo));
-      }
-      const float m_new = fmaxf(m_run, bmax);
-      // lazy rescale: keep a stale max while exp2 stays below 2^8 (same decision in both threads of a row)
-      const bool need = (m_new - m_run) * sl2 > 8.0f;
-      if (__any_sync(0xffffffffu, need)) {
-        float factor = 1.0f;
-        if (need) {
-          factor = ex2_approx((m_run - m_new) * sl2);  // 0 on the first block
-          m_run = m_new;
-          l_run *= factor;
+          for (int i = 0; i < COLS; ++i)
+            if (i >= kv_valid) s[i] = __float_as_uint(-INFINITY);
         }
-        if (j > 0) {
-#pragma unroll 1
-          for (int c = 0; c < COLS / 32; ++c) {
-            uint32_t o[32];
-            tmem_ld32(tO + c * 32, o);
-            tc_wait_ld();
+        // row max over my columns: four independent 3-input max chains
+        float bm0 = -INFINITY, bm1 = -INFINITY, bm2 = -INFINITY, bm3 = -INFINITY;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
-            tmem_st32(tO + c * 32, o);
+        for (int i = 0; i < COLS; i += 8) {
+          bm0 = fmax3(bm0, __uint_as_float(s[i + 0]), __uint_as_float(s[i + 1]));
+          bm1 = fmax3(bm1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
+          bm2 = fmax3(bm2, __uint_as_float(s[i + 4]), __uint_as_float(s[i + 5]));
+          bm3 = fmax3(bm3, __uint_as_float(s[i + 6]), __uint_as_float(s[i + 7]));
+        }
+        float bmax = fmaxf(fmaxf(bm0, bm1), fmaxf(bm2, bm3));
+        if (RPT == 2) {  // both threads of the row must use the same reference
+          const uint32_t xo = (j & 1) * 2048;
+          st_shared_f32(x_mine + xo, bmax);
+          named_bar_sync(xbar, 64);
+          bmax = fmaxf(bmax, ld_shared_f32(x_other + xo));
+        }
+        const float m_new = fmaxf(m_run[t], bmax);
+        // lazy rescale: keep a stale max while exp2 stays below 2^8 (same decision in both threads of a row)
+        const bool need = (m_new - m_run[t]) * sl2 > 8.0f;
+        if (__any_sync(0xffffffffu, need)) {
+          float factor = 1.0f;
+          if (need) {
+            factor = ex2_approx((m_run[t] - m_new) * sl2);  // 0 on the first block
+            m_run[t] = m_new;
+            l_run[t] *= factor;
+          }
+          if (j > 0) {
+#pragma unroll 1
+            for (int c = 0; c < COLS / 32; ++c) {
+              uint32_t o[32];
+              tmem_ld32(tO + c * 32, o);
+              tc_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
+              tmem_st32(tO + c * 32, o);
+            }
           }
         }
+        const float nmb = -m_run[t] * sl2;
+        if (TRACE && tr && j < 64) tr[(j * 2 + g) * 8 + 2] = clock64();
+        if (PP && !COOP) named_bar_sync(1 + g, SM_THREADS);  // wait for this tile's turn on the MUFU
+        if (TRACE && tr && j < 64) tr[(j * 2 + g) * 8 + 3] = clock64();
+        softmax_exp_store<POLY_MASK, NHAND, COLS / 16>(s, tP, sl2, nmb, l_run[t], lane, arrive_p);
+        if (TRACE && tr && j < 64) tr[(j * 2 + g) * 8 + 4] = clock64();
+        if (PP && !COOP) named_bar_arrive(2 - g, SM_THREADS);  // hand the MUFU to the other tile
+        tc_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) arrive_p(NHAND - 1);
+        if (TRACE && tr && j < 64) tr[(j * 2 + g) * 8 + 5] = clock64();
       }
-      const float nmb = -m_run * sl2;
-      if (TRACE && tr && j < 64) tr[(j * 2 + g) * 8 + 2] = clock64();
-      if (PP) named_bar_sync(1 + g, SM_THREADS);  // wait for this tile's turn on the MUFU
-      if (TRACE && tr && j < 64) tr[(j * 2 + g) * 8 + 3] = clock64();
-      softmax_exp_store<POLY_MASK, NHAND, COLS / 16>(s, tP, sl2, nmb, l_run, lane, arrive_p);
-      if (TRACE && tr && j < 64) tr[(j * 2 + g) * 8 + 4] = clock64();
-      if (PP) named_bar_arrive(2 - g, SM_THREADS);  // hand the MUFU to the other tile
-      tc_wait_st();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) arrive_p(NHAND - 1);
-      if (TRACE && tr && j < 64) tr[(j * 2 + g) * 8 + 5] = clock64();
     }
 
-    float l_row = l_run;
-    if (RPT == 2) {  // row sum = my half + the partner's half (both accumulated against the same running max)
-      const uint32_t xo = (P.nkv & 1) * 2048;
-      st_shared_f32(x_mine + xo, l_run);
-      named_bar_sync(xbar, 64);
-      l_row += ld_shared_f32(x_other + xo);
-    }
-
-    // epilogue: O / l -> bf16 -> global (my COLS of the 128 head-dim columns)
-    mbar_wait(&o_done[g], 0);
-    tc_fence_after();
-    const int l = q_row0 + g * TQ + r;
-    const int b = bh / P.H;
-    const int hd = bh - b * P.H;
-    bf16* dst = nullptr;
-    if (l < P.L) {
-      if (l < P.l_split)
-        dst = P.out_a + (static_cast<long long>(b) * P.l_split + l) * P.ld_a + hd * HD + h * COLS;
-      else
-        dst = P.out_b + (static_cast<long long>(b) * (P.L - P.l_split) + (l - P.l_split)) * P.ld_b + hd * HD + h * COLS;
-    }
-    const float inv = 1.0f / l_row;
-#pragma unroll 1
-    for (int c = 0; c < COLS / 32; ++c) {
-      uint32_t o[32];
-      tmem_ld32(tO + c * 32, o);
-      tc_wait_ld();
-      if (dst) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          uint4 u;
-          u.x = pack_bf16(__uint_as_float(o[i * 8 + 0]) * inv, __uint_as_float(o[i * 8 + 1]) * inv);
-          u.y = pack_bf16(__uint_as_float(o[i * 8 + 2]) * inv, __uint_as_float(o[i * 8 + 3]) * inv);
-          u.z = pack_bf16(__uint_as_float(o[i * 8 + 4]) * inv, __uint_as_float(o[i * 8 + 5]) * inv);
-          u.w = pack_bf16(__uint_as_float(o[i * 8 + 6]) * inv, __uint_as_float(o[i * 8 + 7]) * inv);
-          *reinterpret_cast<uint4*>(dst + c * 32 + i * 8) = u;
+    for (int t = 0; t < NT; ++t) {
+      const int g = g_first + t;
+      const uint32_t tO = TM_O + g * 128 + h * COLS + lane_off;
+      float l_row = l_run[t];
+      if (RPT == 2) {  // row sum = my half + the partner's half (both accumulated against the same running max)
+        const uint32_t x_mine = smem_u32(smem + Cfg::XCH_OFF) + ((g * 2 + h) * 128 + r) * 4;
+        const uint32_t x_other = smem_u32(smem + Cfg::XCH_OFF) + ((g * 2 + (1 - h)) * 128 + r) * 4;
+        const uint32_t xo = (P.nkv & 1) * 2048;
+        st_shared_f32(x_mine + xo, l_run[t]);
+        named_bar_sync(3 + g * 4 + q, 64);
+        l_row += ld_shared_f32(x_other + xo);
+      }
+
+      // epilogue: O / l -> bf16 -> global (my COLS of the 128 head-dim columns)
+      mbar_wait(&o_done[g], 0);
+      tc_fence_after();
+      const int l = q_row0 + g * TQ + r;
+      const int b = bh / P.H;
+      const int hd = bh - b * P.H;
+      bf16* dst = nullptr;
+      if (l < P.L) {
+        if (l < P.l_split)
+          dst = P.out_a + (static_cast<long long>(b) * P.l_split + l) * P.ld_a + hd * HD + h * COLS;
+        else
+          dst = P.out_b + (static_cast<long long>(b) * (P.L - P.l_split) + (l - P.l_split)) * P.ld_b + hd * HD + h * COLS;
+      }
+      const float inv = 1.0f / l_row;
+#pragma unroll 1
+      for (int c = 0; c < COLS / 32; ++c) {
+        uint32_t o[32];
+        tmem_ld32(tO + c * 32, o);
+        tc_wait_ld();
+        if (dst) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 u;
+            u.x = pack_bf16(__uint_as_float(o[i * 8 + 0]) * inv, __uint_as_float(o[i * 8 + 1]) * inv);
+            u.y = pack_bf16(__uint_as_float(o[i * 8 + 2]) * inv, __uint_as_float(o[i * 8 + 3]) * inv);
+            u.z = pack_bf16(__uint_as_float(o[i * 8 + 4]) * inv, __uint_as_float(o[i * 8 + 5]) * inv);
+            u.w = pack_bf16(__uint_as_float(o[i * 8 + 6]) * inv, __uint_as_float(o[i * 8 + 7]) * inv);
+            *reinterpret_cast<uint4*>(dst + c * 32 + i * 8) = u;
+          }
         }
       }
     }
@@ -529,6 +547,9 @@ struct AttnVariant {
 #define FB_ATTN_VARIANT(PAIR, POLY, NHAND, PP, RPT, WHAT)                                              \
   {attention_tcgen05_kernel<PAIR, POLY, NHAND, PP, RPT, false>,                                        \
    attention_tcgen05_kernel<PAIR, POLY, NHAND, PP, RPT, true>, PAIR ? 1 : 0, (8 * RPT + 4) * 32, WHAT}
+#define FB_ATTN_VARIANT_COOP(PAIR, POLY, WHAT)                                                         \
+  {attention_tcgen05_kernel<PAIR, POLY, 1, false, 2, false, true>,                                     \
+   attention_tcgen05_kernel<PAIR, POLY, 1, false, 2, true, true>, PAIR ? 1 : 0, 12 * 32, WHAT}
 // run-time selectable builds of the kernel ("attn_variant" flag); index 0 is the production default
 static const AttnVariant kAttnVariants[] = {
     FB_ATTN_VARIANT(false, 0x88, 1, true, 1, "1 CTA, every 4th exp2 pair on the FMA pipe, whole-P handoff"),
@@ -540,6 +561,9 @@ static const AttnVariant kAttnVariants[] = {
     FB_ATTN_VARIANT(false, 0x92, 1, true, 1, "1 CTA, 3 of 8 exp2 pairs on the FMA pipe"),
     FB_ATTN_VARIANT(false, 0xDA, 1, true, 1, "1 CTA, 5 of 8 exp2 pairs on the FMA pipe"),
     FB_ATTN_VARIANT(false, 0xAA, 1, false, 1, "1 CTA, poly 1/2, no MUFU ping-pong"),
+    FB_ATTN_VARIANT_COOP(false, 0x88, "1 CTA, 8 softmax warps serve both tiles (half a row per thread), poly 1/4"),
+    FB_ATTN_VARIANT_COOP(false, 0, "1 CTA, cooperative softmax warps, all exp2 on the MUFU"),
+    FB_ATTN_VARIANT_COOP(true, 0x88, "CTA pair, cooperative softmax warps, poly 1/4"),
 };
 static constexpr int kNumAttnVariants = sizeof(kAttnVariants) / sizeof(kAttnVariants[0]);
 

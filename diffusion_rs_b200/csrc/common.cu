@@ -107,7 +107,7 @@ int get_flag(const char* name) {
   if (!strcmp(name, "gemm_big")) {
     if (g_flag_big < 0) {
       const char* e = getenv("FLUXB200_GEMM_BIG");
-      g_flag_big = e ? atoi(e) : 1;
+      g_flag_big = e ? atoi(e) : 0;  // off by default: measured slower
     }
     return g_flag_big;
   }

@@ -1,6 +1,8 @@
 // fluxb200 — HBM-bound warp-reduction / elementwise kernels of the DiT step.
 // Each kernel fuses what the reference runs as a chain of separate bf16 tensor ops and keeps the
 // reference's rounding points (f32 op -> round-to-nearest-even bf16 after every tensor op).
+#include <algorithm>
+
 #include "internal.h"
 #include "kernels.h"
 #include "ptx.cuh"
@@ -28,97 +30,134 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 // reference: nn::LayerNorm fast path (nn/ops.rs:1021-1043 / reduce.cu:73-131) then ModulationOut::scale_shift
 // (models/flux/model.rs:217-221). One warp per row, the row stays in registers between the two passes.
 // ------------------------------------------------------------------------------------------------
+// Up to two row segments per launch (the img and the txt stream of a double block share it): segment s covers rows
+// [row_begin_s, row_begin_{s+1}) of the launch, reads x_s and its own shift/scale vectors; the output rows of the launch
+// are contiguous.
+struct LnSegment {
+  const bf16* x;
+  const bf16* shift;
+  const bf16* scale;
+  long long in_bstride_rows;
+  int in_row_off, rows_per_batch, row_begin, pad_;
+};
+struct LnParams {
+  LnSegment seg[2];
+  int nseg, total_rows;
+  long long mod_bstride;
+  bf16* out;
+  float eps;
+  const int* step_ptr;
+  long long step_stride;
+};
+
+// One warp per row, the row stays in registers between the two passes; a warp walks rows with the stride of the whole
+// grid, which is sized to exactly fill the machine (4 blocks of 4 warps per SM): 4608 rows over 2368 warps is two
+// balanced rounds, where one row per warp left a 15 %-full second wave.
 template <int D>
-__global__ void __launch_bounds__(128, 4) ln_modulate_kernel(const bf16* __restrict__ x, long long in_bstride_rows,
-                                                          int in_row_off, int rows_per_batch, int total_rows,
-                                                          const bf16* __restrict__ shift,
-                                                          const bf16* __restrict__ scale, long long mod_bstride,
-                                                          bf16* __restrict__ out, float eps,
-                                                          const int* __restrict__ step_ptr, long long step_stride) {
+__global__ void __launch_bounds__(128, 4) ln_modulate_kernel(const __grid_constant__ LnParams P) {
   constexpr int VEC = D / 256;  // uint4 (8 bf16) per lane
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = blockIdx.x * 4 + warp;
   pdl_launch_dependents();
   pdl_wait();  // x is the previous kernel's output
-  if (row >= total_rows) return;
-  const int b = row / rows_per_batch;
-  const int i = row - b * rows_per_batch;
-  const bf16* xr = x + (static_cast<long long>(b) * in_bstride_rows + in_row_off + i) * D;
-  uint4 u[VEC];  // the row stays packed in registers (48 regs) so that >= 5 blocks fit on an SM
-#pragma unroll
-  for (int k = 0; k < VEC; ++k) u[k] = *reinterpret_cast<const uint4*>(xr + (k * 32 + lane) * 8);
-  // The kernel was instruction-bound (~15 instructions per element at 31 rows per SM), not memory-bound: both passes
-  // now run on packed pairs — f32x2 add/fma for the statistics and the normalisation, then the modulate chain in
-  // bf16x2 (an HMUL2/HADD2.BF16 is exactly "f32 op, round to nearest even", the reference's per-op rounding).
-  float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-#pragma unroll
-  for (int k = 0; k < VEC; ++k) {
-    const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float lo = bf_lo(w[e]), hi = bf_hi(w[e]);
-      asm("{\n\t.reg .b64 a, v;\n\tmov.b64 a, {%0, %1};\n\tmov.b64 v, {%2, %3};\n\tadd.rn.f32x2 a, a, v;\n\t"
-          "mov.b64 {%0, %1}, a;\n\t}"
-          : "+f"(s0), "+f"(s1)
-          : "f"(lo), "f"(hi));
-      asm("{\n\t.reg .b64 a, v;\n\tmov.b64 a, {%0, %1};\n\tmov.b64 v, {%2, %3};\n\tfma.rn.f32x2 a, v, v, a;\n\t"
-          "mov.b64 {%0, %1}, a;\n\t}"
-          : "+f"(q0), "+f"(q1)
-          : "f"(lo), "f"(hi));
-    }
-  }
-  const float s = warp_sum(s0 + s1);
-  const float s2 = warp_sum(q0 + q1);
-  const float mean = s / D;
-  const float var = s2 / D - mean * mean;
-  const float inv_std = 1.0f / sqrtf(var + eps);
-  const float nmean = -mean;
   // denoising loop: the modulation vectors of ALL steps were projected before the loop ([step][batch][...]); the
   // current step comes from a device counter so that one captured CUDA graph serves every step
-  const long long mod_off = static_cast<long long>(b) * mod_bstride + (step_ptr ? *step_ptr * step_stride : 0);
-  const bf16* sh = shift + mod_off;
-  const bf16* sc = scale + mod_off;
-  bf16* orow = out + static_cast<long long>(row) * D;
+  const long long step_off = P.step_ptr ? *P.step_ptr * P.step_stride : 0;
   const __nv_bfloat162 one2 = __float2bfloat162_rn(1.0f);
+  for (int row = blockIdx.x * 4 + warp; row < P.total_rows; row += gridDim.x * 4) {
+    const LnSegment& sg = P.seg[(P.nseg > 1 && row >= P.seg[1].row_begin) ? 1 : 0];
+    const int lr = row - sg.row_begin;
+    const int b = lr / sg.rows_per_batch;
+    const int i = lr - b * sg.rows_per_batch;
+    const bf16* xr = sg.x + (static_cast<long long>(b) * sg.in_bstride_rows + sg.in_row_off + i) * D;
+    uint4 u[VEC];  // the row stays packed in registers (48 regs)
 #pragma unroll
-  for (int k = 0; k < VEC; ++k) {
-    const int c = (k * 32 + lane) * 8;
-    const uint4 fs = *reinterpret_cast<const uint4*>(sh + c);
-    const uint4 fc = *reinterpret_cast<const uint4*>(sc + c);
-    const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
-    const uint32_t ws[4] = {fs.x, fs.y, fs.z, fs.w};
-    const uint32_t wc[4] = {fc.x, fc.y, fc.z, fc.w};
-    uint32_t o[4];
+    for (int k = 0; k < VEC; ++k) u[k] = *reinterpret_cast<const uint4*>(xr + (k * 32 + lane) * 8);
+    // The kernel was instruction-bound (~15 instructions per element), not memory-bound: both passes run on packed
+    // pairs - f32x2 add/fma for the statistics and the normalisation, then the modulate chain in bf16x2 (an
+    // HMUL2/HADD2.BF16 is exactly "f32 op, round to nearest even", the reference's per-op rounding).
+    float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      float y0 = bf_lo(w[e]), y1 = bf_hi(w[e]);
-      // (v - mean) * inv_std in f32, two roundings like the reference's fused kernel, on both lanes at once
-      asm("{\n\t.reg .b64 v, m, r;\n\tmov.b64 v, {%0, %1};\n\tmov.b64 m, {%2, %2};\n\tmov.b64 r, {%3, %3};\n\t"
-          "add.rn.f32x2 v, v, m;\n\tmul.rn.f32x2 v, v, r;\n\tmov.b64 {%0, %1}, v;\n\t}"
-          : "+f"(y0), "+f"(y1)
-          : "f"(nmean), "f"(inv_std));
-      const __nv_bfloat162 n2 = __floats2bfloat162_rn(y0, y1);                               // LN -> bf16
-      const __nv_bfloat162 sc1 = __hadd2_rn(*reinterpret_cast<const __nv_bfloat162*>(&wc[e]), one2);  // scale + 1 -> bf16
-      const __nv_bfloat162 m2 = __hmul2_rn(n2, sc1);                                           // * -> bf16
-      const __nv_bfloat162 o2 = __hadd2_rn(m2, *reinterpret_cast<const __nv_bfloat162*>(&ws[e]));  // + shift -> bf16
-      o[e] = *reinterpret_cast<const uint32_t*>(&o2);
+    for (int k = 0; k < VEC; ++k) {
+      const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float lo = bf_lo(w[e]), hi = bf_hi(w[e]);
+        asm("{\n\t.reg .b64 a, v;\n\tmov.b64 a, {%0, %1};\n\tmov.b64 v, {%2, %3};\n\tadd.rn.f32x2 a, a, v;\n\t"
+            "mov.b64 {%0, %1}, a;\n\t}"
+            : "+f"(s0), "+f"(s1)
+            : "f"(lo), "f"(hi));
+        asm("{\n\t.reg .b64 a, v;\n\tmov.b64 a, {%0, %1};\n\tmov.b64 v, {%2, %3};\n\tfma.rn.f32x2 a, v, v, a;\n\t"
+            "mov.b64 {%0, %1}, a;\n\t}"
+            : "+f"(q0), "+f"(q1)
+            : "f"(lo), "f"(hi));
+      }
     }
-    *reinterpret_cast<uint4*>(orow + c) = make_uint4(o[0], o[1], o[2], o[3]);
+    const float s = warp_sum(s0 + s1);
+    const float s2 = warp_sum(q0 + q1);
+    const float mean = s / D;
+    const float var = s2 / D - mean * mean;
+    const float inv_std = 1.0f / sqrtf(var + P.eps);
+    const float nmean = -mean;
+    const long long mod_off = static_cast<long long>(b) * P.mod_bstride + step_off;
+    const bf16* sh = sg.shift + mod_off;
+    const bf16* sc = sg.scale + mod_off;
+    bf16* orow = P.out + static_cast<long long>(row) * D;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      const int c = (k * 32 + lane) * 8;
+      const uint4 fs = *reinterpret_cast<const uint4*>(sh + c);
+      const uint4 fc = *reinterpret_cast<const uint4*>(sc + c);
+      const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+      const uint32_t ws[4] = {fs.x, fs.y, fs.z, fs.w};
+      const uint32_t wc[4] = {fc.x, fc.y, fc.z, fc.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float y0 = bf_lo(w[e]), y1 = bf_hi(w[e]);
+        // (v - mean) * inv_std in f32, two roundings like the reference's fused kernel, on both lanes at once
+        asm("{\n\t.reg .b64 v, m, r;\n\tmov.b64 v, {%0, %1};\n\tmov.b64 m, {%2, %2};\n\tmov.b64 r, {%3, %3};\n\t"
+            "add.rn.f32x2 v, v, m;\n\tmul.rn.f32x2 v, v, r;\n\tmov.b64 {%0, %1}, v;\n\t}"
+            : "+f"(y0), "+f"(y1)
+            : "f"(nmean), "f"(inv_std));
+        const __nv_bfloat162 n2 = __floats2bfloat162_rn(y0, y1);                               // LN -> bf16
+        const __nv_bfloat162 sc1 = __hadd2_rn(*reinterpret_cast<const __nv_bfloat162*>(&wc[e]), one2);  // scale + 1 -> bf16
+        const __nv_bfloat162 m2 = __hmul2_rn(n2, sc1);                                           // * -> bf16
+        const __nv_bfloat162 o2 = __hadd2_rn(m2, *reinterpret_cast<const __nv_bfloat162*>(&ws[e]));  // + shift -> bf16
+        o[e] = *reinterpret_cast<const uint32_t*>(&o2);
+      }
+      *reinterpret_cast<uint4*>(orow + c) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
   }
+}
+
+int launch_ln_modulate2(const LnInput* in, int nseg, long long mod_bstride, bf16* out, int D, float eps,
+                        cudaStream_t stream, const int* step_ptr, long long step_stride) {
+  FB_REQUIRE(D == 3072, "ln_modulate: hidden size must be 3072 (HIDDEN_SIZE, model.rs:17)");
+  FB_REQUIRE(nseg == 1 || nseg == 2, "ln_modulate: 1 or 2 segments");
+  LnParams P{};
+  int rows = 0;
+  for (int s = 0; s < nseg; ++s) {
+    LnSegment& g = P.seg[s];
+    g.x = in[s].x, g.shift = in[s].shift, g.scale = in[s].scale;
+    g.in_bstride_rows = in[s].in_bstride_rows, g.in_row_off = in[s].in_row_off, g.rows_per_batch = in[s].rows_per_batch;
+    g.row_begin = rows;
+    rows += in[s].rows_per_batch * in[s].batch;
+  }
+  P.nseg = nseg, P.total_rows = rows, P.mod_bstride = mod_bstride, P.out = out, P.eps = eps;
+  P.step_ptr = step_ptr, P.step_stride = step_stride;
+  ProfScope _ps(KK_LN_MOD, 0, 4.0 * rows * D, stream);
+  count_launch(KK_LN_MOD, 1);
+  const int grid = std::min((rows + 3) / 4, 4 * num_sms());
+  FB_CHECK_CUDA(launch_ex(ln_modulate_kernel<3072>, dim3(grid), dim3(128), 0, stream, 1, get_flag("pdl") != 0, P));
+  FB_CHECK_CUDA(cudaGetLastError());
+  return 0;
 }
 
 int launch_ln_modulate(const bf16* x, long long in_bstride_rows, int in_row_off, int rows_per_batch, int batch,
                        const bf16* shift, const bf16* scale, long long mod_bstride, bf16* out, int D, float eps,
                        cudaStream_t stream, const int* step_ptr, long long step_stride) {
-  FB_REQUIRE(D == 3072, "ln_modulate: hidden size must be 3072 (HIDDEN_SIZE, model.rs:17)");
-  const int total = rows_per_batch * batch;
-  ProfScope _ps(KK_LN_MOD, 0, 4.0 * total * D, stream);
-  count_launch(KK_LN_MOD, 1);
-  FB_CHECK_CUDA(launch_ex(ln_modulate_kernel<3072>, dim3((total + 3) / 4), dim3(128), 0, stream, 1, get_flag("pdl") != 0,
-                          x, in_bstride_rows, in_row_off, rows_per_batch, total, shift, scale, mod_bstride, out, eps,
-                          step_ptr, step_stride));
-  FB_CHECK_CUDA(cudaGetLastError());
-  return 0;
+  LnInput in{x, shift, scale, in_bstride_rows, in_row_off, rows_per_batch, batch};
+  return launch_ln_modulate2(&in, 1, mod_bstride, out, D, eps, stream, step_ptr, step_stride);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -847,6 +847,12 @@ static int step_core(fluxb200_model* m, const Workspace& w, const bf16* img_in, 
     return launch_ln_modulate(x, in_bstride_rows, in_row_off, rows_per_batch, B, modp(job, shift_chunk),
                               modp(job, scale_chunk), mstride, out, D, eps, st, step_ptr, sstride);
   };
+  // img and txt stream of a double block in one launch: output rows [img | txt] = w.xm
+  auto ln_mod2 = [&](const bf16* ximg, const bf16* xtxt, int ji, int jt, int shift_chunk, int scale_chunk) {
+    LnInput in[2] = {{ximg, modp(ji, shift_chunk), modp(ji, scale_chunk), l_img, 0, l_img, B},
+                     {xtxt, modp(jt, shift_chunk), modp(jt, scale_chunk), l_txt, 0, l_txt, B}};
+    return launch_ln_modulate2(in, 2, mstride, w.xm, D, eps, st, step_ptr, sstride);
+  };
   auto gated = [&](GemmDesc& g, int job, int gate_chunk, int rows_per_batch, const bf16* res) {
     g.gate = modp(job, gate_chunk), g.gate_bstride = mstride, g.rows_per_batch = rows_per_batch, g.res = res;
     g.step_ptr = step_ptr, g.gate_step_stride = sstride;
@@ -869,8 +875,7 @@ static int step_core(fluxb200_model* m, const Workspace& w, const bf16* img_in, 
     bf16* xm_txt = w.xm + static_cast<size_t>(Mi) * D;
     bf16* qkv_img = w.qkv;
     bf16* qkv_txt = w.qkv + static_cast<size_t>(Mi) * 3 * D;
-    TRY(ln_mod(w.img, l_img, 0, l_img, ji, 0, 1, xm_img));
-    TRY(ln_mod(txt_cur, l_txt, 0, l_txt, jt, 0, 1, xm_txt));
+    TRY(ln_mod2(w.img, txt_cur, ji, jt, 0, 1));
     // img and txt problems share one launch when both weights are dense; a quantised weight goes through the (reused)
     // staging buffer, so those problems are launched one by one right after their expansion
     auto two = [&](FusedLinear& fi, FusedLinear& ft, GemmDesc& gi, GemmDesc& gt) -> int {
@@ -920,8 +925,7 @@ static int step_core(fluxb200_model* m, const Workspace& w, const bf16* img_in, 
       txt_cur = w.txt;
     }
     // MLP: x += gate2 * lin2(gelu(lin1(modulate2(LN(x)))))
-    TRY(ln_mod(w.img, l_img, 0, l_img, ji, 3, 4, xm_img));
-    TRY(ln_mod(w.txt, l_txt, 0, l_txt, jt, 3, 4, xm_txt));
+    TRY(ln_mod2(w.img, w.txt, ji, jt, 3, 4));
     bf16* h_img = w.big;
     bf16* h_txt = w.big + static_cast<size_t>(Mi) * MLP_D;
     {

@@ -14,6 +14,16 @@ struct StepScalars {
 int launch_ln_modulate(const bf16* x, long long in_bstride_rows, int in_row_off, int rows_per_batch, int batch,
                        const bf16* shift, const bf16* scale, long long mod_bstride, bf16* out, int D, float eps,
                        cudaStream_t stream, const int* step_ptr = nullptr, long long step_stride = 0);
+// two row segments (the img and txt streams of a double block) in one launch; output rows are contiguous
+struct LnInput {
+  const bf16* x;
+  const bf16* shift;
+  const bf16* scale;
+  long long in_bstride_rows;
+  int in_row_off, rows_per_batch, batch;
+};
+int launch_ln_modulate2(const LnInput* in, int nseg, long long mod_bstride, bf16* out, int D, float eps,
+                        cudaStream_t stream, const int* step_ptr = nullptr, long long step_stride = 0);
 int launch_qknorm_rope(const bf16* qkv, long long ld, int rows_per_batch, int batch, int H, int L, int l_off,
                        const bf16* wq, const bf16* wk, const bf16* pe_cos, const bf16* pe_sin, long long pe_bstride,
                        bf16* Q, bf16* K, bf16* V, float eps, cudaStream_t stream);

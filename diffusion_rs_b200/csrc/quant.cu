@@ -182,95 +182,107 @@ __device__ __forceinline__ void q4k_scale_min(const uint8_t* sc, int is, float d
   m = __fmul_rn(dmin, static_cast<float>(mm));
 }
 
-// <= 40 registers so that a block co-resides with the persistent GEMM CTA of its SM (320 threads x 168 registers): the
-// expansion of the NEXT weight runs on a side stream while the tensor cores work on the current one
+// Persistent: ONE 256-thread block per SM (<= 40 registers per thread) walks all members with a grid stride, so that it
+// co-resides with the persistent GEMM CTA of its SM (320 threads x 168 registers, ~198 KB of shared memory): the
+// expansion of the NEXT weight runs on a side stream while the tensor cores work on the current one.  (A grid of
+// thousands of small blocks would fill the SMs first and keep the GEMM's CTAs from launching until it had drained.)
 __global__ void __launch_bounds__(256, 6) dequant_batch_kernel(const DequantBatch batch) {
   __shared__ float2 lut2[256];
-  const DequantJob& j = batch.job[blockIdx.y];
-  if (j.kind == QB_NF4 || j.kind == QB_FP4) {
-    const float* cb = j.kind == QB_NF4 ? kNF4 : kFP4;
-    lut2[threadIdx.x] = make_float2(cb[threadIdx.x >> 4], cb[threadIdx.x & 15]);
-    __syncthreads();
-    // unit = 4 packed bytes -> 8 weights (16 bytes of bf16)
-    const long long units = j.n / 8;
-    const int bs_units = j.blocksize / 8;  // units per absmax entry (blocksize is a power of two >= 64)
-    constexpr int IT = 4;
-    const long long base = static_cast<long long>(blockIdx.x) * (256 * IT) + threadIdx.x;
-    uint32_t pk[IT];
-    float am[IT];
-#pragma unroll
-    for (int it = 0; it < IT; ++it) {
-      const long long u = base + it * 256;
-      pk[it] = u < units ? __ldg(reinterpret_cast<const uint32_t*>(j.packed) + u) : 0u;
-      am[it] = u < units ? __ldg(j.absmax + u / bs_units) : 0.f;
+  constexpr int IT = 8;
+  const long long stride = static_cast<long long>(gridDim.x) * (256 * IT);
+  int lut_kind = 0;
+  for (int mi = 0; mi < batch.count; ++mi) {
+    const DequantJob& j = batch.job[mi];
+    if ((j.kind == QB_NF4 || j.kind == QB_FP4) && j.kind != lut_kind) {
+      __syncthreads();
+      const float* cb = j.kind == QB_NF4 ? kNF4 : kFP4;
+      lut2[threadIdx.x] = make_float2(cb[threadIdx.x >> 4], cb[threadIdx.x & 15]);
+      __syncthreads();
+      lut_kind = j.kind;
     }
+    if (j.kind == QB_NF4 || j.kind == QB_FP4) {
+      // unit = 4 packed bytes -> 8 weights (16 bytes of bf16)
+      const long long units = j.n / 8;
+      const int bs_units = j.blocksize / 8;  // units per absmax entry (blocksize is a power of two >= 64)
+      for (long long base = static_cast<long long>(blockIdx.x) * (256 * IT) + threadIdx.x; base < units; base += stride) {
+        uint32_t pk[IT];
+        float am[IT];
 #pragma unroll
-    for (int it = 0; it < IT; ++it) {
-      const long long u = base + it * 256;
-      if (u >= units) break;
-      uint4 o;
-      float2 c;
-      c = lut2[pk[it] & 0xffu];         o.x = pack_bf16(c.x * am[it], c.y * am[it]);
-      c = lut2[(pk[it] >> 8) & 0xffu];  o.y = pack_bf16(c.x * am[it], c.y * am[it]);
-      c = lut2[(pk[it] >> 16) & 0xffu]; o.z = pack_bf16(c.x * am[it], c.y * am[it]);
-      c = lut2[pk[it] >> 24];           o.w = pack_bf16(c.x * am[it], c.y * am[it]);
-      reinterpret_cast<uint4*>(j.out)[u] = o;
-    }
-  } else if (j.kind == QB_INT8) {
-    // unit = 8 int8 weights -> 16 bytes of bf16
-    const long long units = j.n / 8;
-    const int col_units = j.col / 8;
-    constexpr int IT = 4;
-    const long long base = static_cast<long long>(blockIdx.x) * (256 * IT) + threadIdx.x;
+        for (int it = 0; it < IT; ++it) {
+          const long long u = base + it * 256;
+          pk[it] = u < units ? __ldg(reinterpret_cast<const uint32_t*>(j.packed) + u) : 0u;
+          am[it] = u < units ? __ldg(j.absmax + u / bs_units) : 0.f;
+        }
 #pragma unroll
-    for (int it = 0; it < IT; ++it) {
-      const long long u = base + it * 256;
-      if (u >= units) break;
-      const uint2 q = __ldg(reinterpret_cast<const uint2*>(j.packed) + u);
-      const float sc = __ldg(j.scb + u / col_units);
-      const uint32_t w2[2] = {q.x, q.y};
-      uint32_t o[4];
-#pragma unroll
-      for (int h = 0; h < 4; ++h) {
-        const int v0 = static_cast<int8_t>((w2[h >> 1] >> (16 * (h & 1))) & 0xffu);
-        const int v1 = static_cast<int8_t>((w2[h >> 1] >> (16 * (h & 1) + 8)) & 0xffu);
-        o[h] = pack_bf16((static_cast<float>(v0) * sc) / 127.f, (static_cast<float>(v1) * sc) / 127.f);
+        for (int it = 0; it < IT; ++it) {
+          const long long u = base + it * 256;
+          if (u >= units) break;
+          uint4 o;
+          float2 c;
+          c = lut2[pk[it] & 0xffu];         o.x = pack_bf16(c.x * am[it], c.y * am[it]);
+          c = lut2[(pk[it] >> 8) & 0xffu];  o.y = pack_bf16(c.x * am[it], c.y * am[it]);
+          c = lut2[(pk[it] >> 16) & 0xffu]; o.z = pack_bf16(c.x * am[it], c.y * am[it]);
+          c = lut2[pk[it] >> 24];           o.w = pack_bf16(c.x * am[it], c.y * am[it]);
+          reinterpret_cast<uint4*>(j.out)[u] = o;
+        }
       }
-      reinterpret_cast<uint4*>(j.out)[u] = make_uint4(o[0], o[1], o[2], o[3]);
-    }
-  } else {
-    // Q4_K: unit = one 64-weight group (32 q bytes): 8 lanes, each 4 q bytes -> 4 low-nibble + 4 high-nibble weights.
-    // blockIdx.x covers 1024 lane-units = 32 super-blocks.
-    const long long nblocks = j.n / 256;
-    constexpr int IT = 4;
-    const long long base = static_cast<long long>(blockIdx.x) * (256 * IT) + threadIdx.x;
+    } else if (j.kind == QB_INT8) {
+      // unit = 8 int8 weights -> 16 bytes of bf16
+      const long long units = j.n / 8;
+      const int col_units = j.col / 8;
+      for (long long base = static_cast<long long>(blockIdx.x) * (256 * IT) + threadIdx.x; base < units; base += stride) {
 #pragma unroll
-    for (int it = 0; it < IT; ++it) {
-      const long long u = base + it * 256;  // lane-unit: super-block u / 32, lane u % 32
-      const long long blk = u >> 5;
-      if (blk >= nblocks) break;
-      const int lane = static_cast<int>(u & 31);
-      const uint8_t* p = j.packed + blk * 144;
-      const float d = __half2float(*reinterpret_cast<const __half*>(p));
-      const float dmin = __half2float(*reinterpret_cast<const __half*>(p + 2));
-      const int g = lane >> 3, off = (lane & 7) * 4;
-      float d1, m1, d2, m2;
-      q4k_scale_min(p + 4, 2 * g, d, dmin, d1, m1);
-      q4k_scale_min(p + 4, 2 * g + 1, d, dmin, d2, m2);
-      const uint32_t q4 = *reinterpret_cast<const uint32_t*>(p + 16 + g * 32 + off);
-      bf16* o = j.out + blk * 256 + g * 64 + off;
-      float lo[4], hi[4];
+        for (int it = 0; it < IT; ++it) {
+          const long long u = base + it * 256;
+          if (u >= units) break;
+          const uint2 q = __ldg(reinterpret_cast<const uint2*>(j.packed) + u);
+          const float sc = __ldg(j.scb + u / col_units);
+          const uint32_t w2[2] = {q.x, q.y};
+          uint32_t o[4];
 #pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        const uint32_t q = (q4 >> (8 * b)) & 0xff;
-        lo[b] = __half2float(__float2half_rn(__fsub_rn(__fmul_rn(d1, static_cast<float>(q & 0xF)), m1)));
-        hi[b] = __half2float(__float2half_rn(__fsub_rn(__fmul_rn(d2, static_cast<float>(q >> 4)), m2)));
+          for (int h = 0; h < 4; ++h) {
+            const int v0 = static_cast<int8_t>((w2[h >> 1] >> (16 * (h & 1))) & 0xffu);
+            const int v1 = static_cast<int8_t>((w2[h >> 1] >> (16 * (h & 1) + 8)) & 0xffu);
+            o[h] = pack_bf16((static_cast<float>(v0) * sc) / 127.f, (static_cast<float>(v1) * sc) / 127.f);
+          }
+          reinterpret_cast<uint4*>(j.out)[u] = make_uint4(o[0], o[1], o[2], o[3]);
+        }
       }
-      uint2 v;
-      v.x = pack_bf16(lo[0], lo[1]), v.y = pack_bf16(lo[2], lo[3]);
-      *reinterpret_cast<uint2*>(o) = v;
-      v.x = pack_bf16(hi[0], hi[1]), v.y = pack_bf16(hi[2], hi[3]);
-      *reinterpret_cast<uint2*>(o + 32) = v;
+    } else {
+      // Q4_K: lane-unit = 4 q bytes of one 64-weight group -> 4 low-nibble + 4 high-nibble weights; 32 lane-units per
+      // 144-byte super-block
+      const long long nblocks = j.n / 256;
+      const long long units = nblocks * 32;
+      for (long long base = static_cast<long long>(blockIdx.x) * (256 * IT) + threadIdx.x; base < units; base += stride) {
+#pragma unroll 2
+        for (int it = 0; it < IT; ++it) {
+          const long long u = base + it * 256;
+          if (u >= units) break;
+          const long long blk = u >> 5;
+          const int lane = static_cast<int>(u & 31);
+          const uint8_t* p = j.packed + blk * 144;
+          const float d = __half2float(*reinterpret_cast<const __half*>(p));
+          const float dmin = __half2float(*reinterpret_cast<const __half*>(p + 2));
+          const int g = lane >> 3, off = (lane & 7) * 4;
+          float d1, m1, d2, m2;
+          q4k_scale_min(p + 4, 2 * g, d, dmin, d1, m1);
+          q4k_scale_min(p + 4, 2 * g + 1, d, dmin, d2, m2);
+          const uint32_t q4 = *reinterpret_cast<const uint32_t*>(p + 16 + g * 32 + off);
+          bf16* o = j.out + blk * 256 + g * 64 + off;
+          float lo[4], hi[4];
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            const uint32_t q = (q4 >> (8 * b)) & 0xff;
+            lo[b] = __half2float(__float2half_rn(__fsub_rn(__fmul_rn(d1, static_cast<float>(q & 0xF)), m1)));
+            hi[b] = __half2float(__float2half_rn(__fsub_rn(__fmul_rn(d2, static_cast<float>(q >> 4)), m2)));
+          }
+          uint2 v;
+          v.x = pack_bf16(lo[0], lo[1]), v.y = pack_bf16(lo[2], lo[3]);
+          *reinterpret_cast<uint2*>(o) = v;
+          v.x = pack_bf16(hi[0], hi[1]), v.y = pack_bf16(hi[2], hi[3]);
+          *reinterpret_cast<uint2*>(o + 32) = v;
+        }
+      }
     }
   }
 }
@@ -302,7 +314,7 @@ int launch_dequant_batch(const DequantBatch& batch, cudaStream_t stream) {
   }
   ProfScope _ps(KK_DEQUANT, 0, bytes, stream);
   count_launch(KK_DEQUANT);
-  const dim3 grid(static_cast<unsigned>((max_units + 1023) / 1024), batch.count);
+  const unsigned grid = static_cast<unsigned>(std::min<long long>((max_units + 2047) / 2048, num_sms()));
   dequant_batch_kernel<<<grid, 256, 0, stream>>>(batch);
   FB_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -63,7 +63,7 @@ def test_linear_big_tiles_bit_identical(fluxlib, M, N, K, flag):
             outs.append(ops.linear(x, w, b, bias_mode=ops.BIAS_FUSED, act=ops.ACT_GELU))
         else:
             outs.append(ops.linear(x, w, b, bias_mode=ops.BIAS_FUSED, gate=gate, rows_per_batch=rpb, res=res))
-    L.check(fluxlib.fluxb200_set_flag(b"gemm_big", 1))
+    L.check(fluxlib.fluxb200_set_flag(b"gemm_big", 0))
     torch.cuda.synchronize()
     assert torch.equal(outs[0], outs[1])
     if flag == 1 and M == 4112:  # and the result is right, not just equal
