@@ -78,11 +78,19 @@ ProfScope::~ProfScope() {
   cudaEventRecord(g_prof_recs[slot].b, stream);
 }
 
-static int g_flag_qkrope = 1, g_flag_pair = -1, g_flag_fdq = 0, g_flag_attn = -1, g_flag_pdl = -1, g_flag_cl4 = -1,
+static int g_flag_qkrope = 1, g_flag_pair = -1, g_flag_dqm = -1, g_flag_attn = -1, g_flag_pdl = -1, g_flag_cl4 = -1,
            g_flag_graph = -1, g_flag_big = -1, g_flag_dqo = -1;
 int get_flag(const char* name) {
   if (!strcmp(name, "qkrope_fusion")) return g_flag_qkrope;
-  if (!strcmp(name, "fused_dequant")) return g_flag_fdq;
+  if (!strcmp(name, "dequant_mode")) {
+    if (g_flag_dqm < 0) {
+      const char* e = getenv("FLUXB200_DEQUANT_MODE");
+      g_flag_dqm = e ? (atoi(e) & 3) : 0;
+      if (g_flag_dqm > 2) g_flag_dqm = 0;
+    }
+    return g_flag_dqm;
+  }
+  if (!strcmp(name, "fused_dequant")) return get_flag("dequant_mode") == 2;
   if (!strcmp(name, "gemm_cl4")) {
     if (g_flag_cl4 < 0) {
       const char* e = getenv("FLUXB200_GEMM_CL4");
@@ -241,7 +249,12 @@ int fluxb200_set_flag(const char* name, int value) {
   if (!name) return fb::fail("set_flag: null name");
   if (!strcmp(name, "qkrope_fusion")) { fb::g_flag_qkrope = value ? 1 : 0; return 0; }
   if (!strcmp(name, "gemm_pair")) { fb::g_flag_pair = value ? 1 : 0; return 0; }
-  if (!strcmp(name, "fused_dequant")) { fb::g_flag_fdq = value ? 1 : 0; return 0; }
+  if (!strcmp(name, "dequant_mode")) {
+    if (value < 0 || value > 2) return fb::fail("set_flag: dequant_mode must be 0 (per-image cache), 1 (staged) or 2 (fused)");
+    fb::g_flag_dqm = value;
+    return 0;
+  }
+  if (!strcmp(name, "fused_dequant")) { fb::g_flag_dqm = value ? 2 : 0; return 0; }  // older name: 1 = fused, 0 = default
   if (!strcmp(name, "attn_variant")) { fb::g_flag_attn = value; return 0; }
   if (!strcmp(name, "pdl")) { fb::g_flag_pdl = value ? 1 : 0; return 0; }
   if (!strcmp(name, "gemm_cl4")) { fb::g_flag_cl4 = value ? 1 : 0; return 0; }

@@ -110,6 +110,7 @@ struct FusedLinear {
   int bias_mode3 = BIAS_FUSED;  // rank-3 call sites: cuBLASLt fused bias (dense) vs separate add (bnb)
   std::vector<Member> members;
   QuantB qb;  // quantised: operand description for the fused-dequant GEMM producer
+  size_t cache_off = 0;  // quantised: element offset of this linear's bf16 expansion inside the per-image weight cache
 };
 
 struct DoubleBlock {
@@ -128,6 +129,7 @@ struct Workspace {
   uint2* pe2;
   bf16 *pe_cos, *pe_sin, *temb, *gemb, *e1, *e2, *e3, *e4, *vec, *svec, *mod_all;
   bf16 *lat, *img, *txt, *x, *xm, *qkv, *Q, *K, *V, *attn_img, *attn_txt, *big, *txt_cache;
+  bf16* wcache;  // denoising loop, quantised models: bf16 expansion of every quantised step weight, valid for one image
   size_t total = 0;
 };
 
@@ -167,6 +169,7 @@ struct fluxb200_model {
   cudaStream_t side_stream = nullptr, cap_side_stream = nullptr;
   cudaEvent_t ev_fork[4] = {nullptr, nullptr, nullptr, nullptr}, ev_ready[2] = {nullptr, nullptr};
   size_t wscratch_elems = 0;
+  size_t wcache_elems = 0;  // sum over worder of N*K
   bool any_quant = false;
   // step graph (denoise): captured on a private stream, replayed on the caller's
   cudaStream_t cap_stream = nullptr;
@@ -379,7 +382,7 @@ static int weight_operand(fluxb200_model* m, const FusedLinear& fl, const bf16**
     *w = fl.w;
     return 0;
   }
-  if (get_flag("fused_dequant") && fused_dequant_ok(fl)) {
+  if (get_flag("dequant_mode") == 2 && fused_dequant_ok(fl)) {
     *w = nullptr;  // gemm_for() switches to the fused-dequant producer
     return 0;
   }
@@ -405,9 +408,21 @@ static int expand_into(const FusedLinear& fl, bf16* stage, cudaStream_t st) {
   return launch_dequant_batch(batch, st);
 }
 
+// ---- the three ways a quantised weight reaches the tensor cores ("dequant_mode" flag) ----
+//   0  per-image cache (default): fluxb200_model_denoise expands every quantised step weight ONCE per call into a bf16
+//      cache carved from the caller's workspace (+ 2 B per quantised weight, 23.8 GB for a fully quantised FLUX.1-dev:
+//      nothing on a 180 GB part) and all steps run the dense GEMMs on it; the resident model stays packed (6 GB)
+//   1  staged per layer: every step expands each weight into an L2-sized staging buffer right before its GEMM, one
+//      weight ahead on a side stream ("dequant_overlap")
+//   2  fused: the GEMM's producer warps expand the packed tile in shared memory (no bf16 copy in HBM at all)
+// Same bits in all three (tests).  A single fluxb200_model_forward has no image to amortise over: it uses 1 (or 2).
+static bool weight_cache_enabled(const fluxb200_model* m) {
+  return m->any_quant && !m->worder.empty() && get_flag("dequant_mode") == 0;
+}
+
 // ---- expansion pipeline (see fluxb200_model::worder) ----
 static bool pipe_enabled(const fluxb200_model* m) {
-  return m->any_quant && !m->worder.empty() && get_flag("dequant_overlap") != 0 && get_flag("fused_dequant") == 0 &&
+  return m->any_quant && !m->worder.empty() && get_flag("dequant_overlap") != 0 && get_flag("dequant_mode") != 2 &&
          !profiling_enabled();
 }
 static void pipe_begin(fluxb200_model* m) { m->wnext = m->wissued = 0; }
@@ -452,7 +467,7 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // `steps` = number of denoising steps whose per-step tables (t, dt, vec_, every modulation vector) live in the
 // workspace: 1 for a single Flux::forward, n_timesteps - 1 for the denoising loop.
-static Workspace carve(const fluxb200_model* m, void* base, int B, int l_img, int l_txt, int steps) {
+static Workspace carve(const fluxb200_model* m, void* base, int B, int l_img, int l_txt, int steps, bool cache = false) {
   Workspace w{};
   uint8_t* p = static_cast<uint8_t*>(base);
   size_t off = 0;
@@ -494,6 +509,7 @@ static Workspace carve(const fluxb200_model* m, void* base, int B, int l_img, in
   w.attn_txt = static_cast<bf16*>(take(Mt * D * 2));
   w.big = static_cast<bf16*>(take(Mx * (D + MLP_D) * 2));  // single: [attn | gelu(mlp)]; double: MLP hidden
   w.txt_cache = static_cast<bf16*>(take(Mt * D * 2));
+  w.wcache = cache ? static_cast<bf16*>(take(m->wcache_elems * 2)) : nullptr;
   w.total = off;
   return w;
 }
@@ -712,6 +728,11 @@ int fluxb200_model_finalize(fluxb200_model* m, fluxb200_stream_t stream) {
   }
   for (auto& b : m->sgl) use(b.lin1), use(b.lin2);
   use(m->final_proj);
+  m->wcache_elems = 0;
+  for (const FusedLinear* fl : m->worder) {
+    const_cast<FusedLinear*>(fl)->cache_off = m->wcache_elems;
+    m->wcache_elems += (static_cast<size_t>(fl->N) * fl->K + 511) / 512 * 512;  // keep every weight 1 KB aligned
+  }
   m->finalized = true;
   return 0;
 #undef TRY
@@ -730,7 +751,7 @@ int fluxb200_model_denoise_workspace_size(const fluxb200_model* m, int32_t batch
   FB_REQUIRE(m && bytes && m->finalized, "denoise_workspace_size: model not finalized");
   FB_REQUIRE(batch >= 1 && batch <= 8 && l_img > 0 && l_txt > 0, "denoise_workspace_size: bad geometry (batch 1..8)");
   FB_REQUIRE(n_timesteps >= 2 && n_timesteps <= MAX_STEPS, "denoise_workspace_size: 2..1024 timesteps");
-  *bytes = carve(m, nullptr, batch, l_img, l_txt, n_timesteps - 1).total + 1024;
+  *bytes = carve(m, nullptr, batch, l_img, l_txt, n_timesteps - 1, weight_cache_enabled(m)).total + 1024;
   return 0;
 }
 
@@ -825,10 +846,16 @@ static int compute_modulations(fluxb200_model* m, const Workspace& w, const floa
 static int step_core(fluxb200_model* m, const Workspace& w, const bf16* img_in, bf16* pred_out, bf16* lat,
                      const int* step_ptr, int B, int l_img, int l_txt, cudaStream_t st, cudaStream_t side) {
   const auto& c = m->cfg;
-  // quantised weights: staged expansion, software-pipelined one weight ahead on the side stream (or in-order on `st`)
-  const bool piped = pipe_enabled(m);
+  // quantised weights: the per-image bf16 cache when the caller's workspace carries one (denoising loop); otherwise
+  // staged expansion, software-pipelined one weight ahead on the side stream (or in-order on `st`), or fused
+  const bf16* const cache = w.wcache;
+  const bool piped = cache == nullptr && pipe_enabled(m);
   pipe_begin(m);
   auto W = [&](const FusedLinear& fl, const bf16** wp) -> int {
+    if (cache && fl.quant) {
+      *wp = cache + fl.cache_off;
+      return 0;
+    }
     if (piped && fl.quant) return pipe_acquire(m, fl, wp, st, side);
     return weight_operand(m, fl, wp, st);
   };
@@ -879,9 +906,11 @@ static int step_core(fluxb200_model* m, const Workspace& w, const bf16* img_in, 
     // img and txt problems share one launch when both weights are dense; a quantised weight goes through the (reused)
     // staging buffer, so those problems are launched one by one right after their expansion
     auto two = [&](FusedLinear& fi, FusedLinear& ft, GemmDesc& gi, GemmDesc& gt) -> int {
-      if (!fi.quant && !ft.quant) {
+      if ((!fi.quant && !ft.quant) || cache) {  // both operands are stable bf16 tensors: one grouped launch
         GemmDesc g[2] = {gi, gt};
-        g[0].w = fi.w, g[1].w = ft.w;
+        if (int r = W(fi, &g[0].w)) return r;
+        if (int r = W(ft, &g[1].w)) return r;
+        g[0].qb = g[1].qb = nullptr;
         return launch_gemm(g, 2, st);
       }
       for (int s = 0; s < 2; ++s) {
@@ -996,7 +1025,7 @@ static int step_core(fluxb200_model* m, const Workspace& w, const bf16* img_in, 
   return 0;
 }
 
-static int check_ws(fluxb200_model* m, int B, int l_img, int l_txt, int steps, void* ws, uint64_t ws_bytes,
+static int check_ws(fluxb200_model* m, int B, int l_img, int l_txt, int steps, bool cache, void* ws, uint64_t ws_bytes,
                     Workspace* out) {
   FB_REQUIRE(m && m->finalized, "model not finalized");
   FB_REQUIRE(B >= 1 && B <= 8, "batch must be in 1..8 per call");
@@ -1004,7 +1033,7 @@ static int check_ws(fluxb200_model* m, int B, int l_img, int l_txt, int steps, v
   FB_REQUIRE(ws != nullptr, "null workspace");
   uint8_t* base = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(ws), 1024));
   const size_t slack = base - static_cast<uint8_t*>(ws);
-  Workspace w = carve(m, base, B, l_img, l_txt, steps);
+  Workspace w = carve(m, base, B, l_img, l_txt, steps, cache);
   FB_REQUIRE(w.total + slack <= ws_bytes, "workspace too small: need " + std::to_string(w.total + 1024) + " bytes");
   *out = w;
   return 0;
@@ -1014,7 +1043,7 @@ static unsigned flags_signature() {
   unsigned s = 0;
   s = s * 2 + (get_flag("qkrope_fusion") & 1);
   s = s * 2 + (get_flag("pdl") & 1);
-  s = s * 2 + (get_flag("fused_dequant") & 1);
+  s = s * 4 + (get_flag("dequant_mode") & 3);
   s = s * 2 + (get_flag("gemm_pair") & 1);
   s = s * 2 + (get_flag("gemm_cl4") & 1);
   s = s * 2 + (get_flag("dequant_overlap") & 1);
@@ -1084,7 +1113,7 @@ int fluxb200_model_forward(fluxb200_model* m, const void* img, const void* img_i
                            uint64_t workspace_bytes, fluxb200_stream_t stream) {
   FB_REQUIRE(img && img_ids && txt && txt_ids && timesteps && y && out, "forward: null tensor");
   Workspace w;
-  if (int rc = check_ws(m, batch, l_img, l_txt, 1, workspace, workspace_bytes, &w)) return rc;
+  if (int rc = check_ws(m, batch, l_img, l_txt, 1, false, workspace, workspace_bytes, &w)) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   StepIO io{static_cast<const bf16*>(img_ids), static_cast<const bf16*>(txt), static_cast<const bf16*>(txt_ids),
             static_cast<const bf16*>(y)};
@@ -1109,7 +1138,7 @@ int fluxb200_model_denoise(fluxb200_model* m, void* img, const void* img_ids, co
   FB_REQUIRE(n_timesteps <= MAX_STEPS, "denoise: at most 1024 timesteps");
   const int steps = n_timesteps - 1;
   Workspace w;
-  if (int rc = check_ws(m, batch, l_img, l_txt, steps, workspace, workspace_bytes, &w)) return rc;
+  if (int rc = check_ws(m, batch, l_img, l_txt, steps, weight_cache_enabled(m), workspace, workspace_bytes, &w)) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   StepIO io{static_cast<const bf16*>(img_ids), static_cast<const bf16*>(txt), static_cast<const bf16*>(txt_ids),
             static_cast<const bf16*>(y)};
@@ -1136,6 +1165,10 @@ int fluxb200_model_denoise(fluxb200_model* m, void* img, const void* img_ids, co
   if (int rc = compute_modulations(m, w, w.t_all, m->cfg.guidance_embeds ? w.g_all : nullptr, io.y, steps * batch,
                                    batch, st))
     return rc;
+  // quantised model: expand every step weight once for the whole image (see weight_cache_enabled)
+  if (w.wcache)
+    for (const FusedLinear* fl : m->worder)
+      if (int rc = expand_into(*fl, w.wcache + fl->cache_off, st)) return rc;
   // ---- the loop: one graph replay per step (or the same kernels launched one by one) ----
   StepGraph* sg = nullptr;
   m->last_used_graph = 0;

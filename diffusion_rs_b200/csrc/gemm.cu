@@ -158,9 +158,11 @@ __device__ __forceinline__ float gelu_bf16_steps(float v) {
 enum { EV_PLAIN = 0, EV_GELU = 1, EV_RES = 2, EV_GATE_RES = 3, EV_ALPHA = 4, EV_KINDS = 5, EV_QKROPE = 5 };  // x bias mode (3)
 
 // 16 consecutive output columns of one row: acc (fp32, from TMEM) -> bf16, fully unrolled, compile-time variant.
+// The residual (the only operand that is unique per element, i.e. a real L2/HBM round trip) arrives in registers: it
+// is prefetched one 32-column chunk ahead by epi_drain, the first chunk even before the accumulator is complete.
 template <int BIAS, int EV>
 __device__ __forceinline__ void epi16(const uint32_t* acc, bf16* outp, const bf16* biasp, const bf16* gatep,
-                                      const bf16* resp, bf162 alpha2) {
+                                      const uint4* resr, bf162 alpha2) {
   uint32_t b[8], g[8], r[8], o[8];
   if (BIAS != BIAS_NONE) {
     *reinterpret_cast<uint4*>(&b[0]) = *reinterpret_cast<const uint4*>(biasp);
@@ -171,8 +173,8 @@ __device__ __forceinline__ void epi16(const uint32_t* acc, bf16* outp, const bf1
     *reinterpret_cast<uint4*>(&g[4]) = *reinterpret_cast<const uint4*>(gatep + 8);
   }
   if (EV == EV_GATE_RES || EV == EV_RES) {
-    *reinterpret_cast<uint4*>(&r[0]) = *reinterpret_cast<const uint4*>(resp);
-    *reinterpret_cast<uint4*>(&r[4]) = *reinterpret_cast<const uint4*>(resp + 8);
+    *reinterpret_cast<uint4*>(&r[0]) = resr[0];
+    *reinterpret_cast<uint4*>(&r[4]) = resr[1];
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -481,10 +483,12 @@ __device__ __forceinline__ void dequant_producer(const GemmParams& P, uint8_t* s
 // ------------------------------------------------------------------------------------------------
 // Epilogue of one 128-row x 256-column accumulator (TMEM columns [t_acc, t_acc + 256)) by the calling warp: lane quarter
 // q = warp % 4 (hardware rule), column half chosen by the warp's index (8 epilogue warps) or both halves in turn (4).
-// The caller has waited for the accumulator; it releases it afterwards.
+// Waits for the accumulator itself (`full_bar` / `parity`) AFTER it has issued the loads of the first residual chunk;
+// the caller releases the accumulator afterwards.
 // ------------------------------------------------------------------------------------------------
 template <int EPI_WARPS, bool QKROPE = true>
-__device__ __forceinline__ void epi_drain(const GemmProblemDev& p, int n_t, int m_t, uint32_t t_acc, int warp, int lane) {
+__device__ __forceinline__ void epi_drain(const GemmProblemDev& p, int n_t, int m_t, uint32_t t_acc, int warp, int lane,
+                                          uint64_t* full_bar, uint32_t parity) {
   const int q = warp & 3;
   const int r = q * 32 + lane;  // row inside the tile == TMEM lane
   long long grow;
@@ -507,6 +511,7 @@ __device__ __forceinline__ void epi_drain(const GemmProblemDev& p, int n_t, int 
                           : 0;
   const bf162 alpha2 = __float2bfloat162_rn(p.alpha);
   const int bias_mode = p.bias_mode;
+  const bool res_ev = valid && (p.ev0 == EV_RES || p.ev0 == EV_GATE_RES);  // only segment 0 can carry a residual
 
   // 8 epilogue warps: each drains one 128-column half; 4 epilogue warps (quantised-B kernel): both halves in turn
 #pragma unroll 1
@@ -515,6 +520,21 @@ __device__ __forceinline__ void epi_drain(const GemmProblemDev& p, int n_t, int 
   const uint32_t t_row = t_acc + chalf * 128 + (static_cast<uint32_t>(q * 32) << 16);
   const int n_half0 = n_t * BLOCK_N + chalf * 128;
   const bool half_seg1 = (p.n_split > 0) && (n_half0 >= p.n_split);
+  // residual of the NEXT 32-column chunk of this thread's row (full chunks of segment 0 only)
+  uint4 rn[4];
+  auto prefetch_res = [&](int chunk) {
+    const int n0 = n_half0 + chunk * 32;
+    if (res_ev && chunk < 4 && n0 + 32 <= p.N && !((p.n_split > 0) && (n0 >= p.n_split))) {
+      const uint4* rp = reinterpret_cast<const uint4*>(p.res + grow * p.ld0 + n0);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) rn[i] = rp[i];
+    }
+  };
+  prefetch_res(0);
+  if (hh == 0) {
+    mbar_wait(full_bar, parity);
+    tc_fence_after();
+  }
   if (QKROPE && p.ev0 == EV_QKROPE && !half_seg1 && n_half0 < p.N) {
     epi_qkrope(p, t_row, n_half0, grow, valid);
   } else
@@ -522,6 +542,8 @@ __device__ __forceinline__ void epi_drain(const GemmProblemDev& p, int n_t, int 
   for (int chunk = 0; chunk < 4; ++chunk) {
     const int n0 = n_t * BLOCK_N + chalf * 128 + chunk * 32;
     if (n0 >= p.N) break;  // warp-uniform
+    const uint4 rc[4] = {rn[0], rn[1], rn[2], rn[3]};
+    prefetch_res(chunk + 1);
     uint32_t acc_r[32];
     tmem_ld32(t_row + chunk * 32, acc_r);
     tc_wait_ld();
@@ -536,9 +558,9 @@ __device__ __forceinline__ void epi_drain(const GemmProblemDev& p, int n_t, int 
       // warp-uniform dispatch to a fully specialised 2 x 16-column body
 #define FB_EPI_CASE(B, E)                                                                  \
   case (B) * EV_KINDS + (E):                                                               \
-epi16<B, E>(acc_r, outp, biasp, gatep, resp, alpha2);                                  \
+epi16<B, E>(acc_r, outp, biasp, gatep, rc, alpha2);                                    \
 epi16<B, E>(acc_r + 16, outp + 16, biasp ? biasp + 16 : nullptr, gatep ? gatep + 16 : nullptr, \
-            resp ? resp + 16 : nullptr, alpha2);                                       \
+            rc + 2, alpha2);                                                           \
 break;
 #define FB_EPI_BIAS(B) \
   FB_EPI_CASE(B, EV_PLAIN) FB_EPI_CASE(B, EV_GELU) FB_EPI_CASE(B, EV_RES) FB_EPI_CASE(B, EV_GATE_RES) FB_EPI_CASE(B, EV_ALPHA)
@@ -806,9 +828,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       TileCoord tc = decode_tile(P, t);
       const GemmProblemDev& p = P.p[tc.prob];
       const int m_t = UNIT_CTAS * tc.m_t + static_cast<int>(rank_cl);
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
-      epi_drain<EPI_WARPS>(p, tc.n_t, m_t, tmem_base + acc * BLOCK_N, warp, lane);
+      epi_drain<EPI_WARPS>(p, tc.n_t, m_t, tmem_base + acc * BLOCK_N, warp, lane, &tmem_full[acc], acc_phase);
       // release the accumulator back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -1004,9 +1024,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_big_kernel(const
       for (int s = 0; s < it.nsub; ++s) {
         const int acc = acc0 + s;
         const int m_t = 2 * (it.blk0 + s) + static_cast<int>(cta_rank);
-        mbar_wait(&tmem_full[acc], (ephase >> acc) & 1u);
-        tc_fence_after();
-        epi_drain<EPI_WARPS, false>(p, it.n_t, m_t, tmem_base + acc * BLOCK_N, warp, lane);
+        epi_drain<EPI_WARPS, false>(p, it.n_t, m_t, tmem_base + acc * BLOCK_N, warp, lane, &tmem_full[acc],
+                                    (ephase >> acc) & 1u);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));

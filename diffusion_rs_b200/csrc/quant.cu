@@ -182,10 +182,9 @@ __device__ __forceinline__ void q4k_scale_min(const uint8_t* sc, int is, float d
   m = __fmul_rn(dmin, static_cast<float>(mm));
 }
 
-// Persistent: ONE 256-thread block per SM (<= 40 registers per thread) walks all members with a grid stride, so that it
-// co-resides with the persistent GEMM CTA of its SM (320 threads x 168 registers, ~198 KB of shared memory): the
-// expansion of the NEXT weight runs on a side stream while the tensor cores work on the current one.  (A grid of
-// thousands of small blocks would fill the SMs first and keep the GEMM's CTAs from launching until it had drained.)
+// Grid-stride over (units, members); <= 40 registers per thread.  (A one-block-per-SM persistent variant, meant to
+// co-reside with the GEMM's CTAs while the expansion runs on a side stream, measured 1.6 TB/s instead of 2.7 and made
+// the overlapped step slower: the expansion became the critical path behind the short txt-stream GEMMs.)
 __global__ void __launch_bounds__(256, 6) dequant_batch_kernel(const DequantBatch batch) {
   __shared__ float2 lut2[256];
   constexpr int IT = 8;
@@ -314,7 +313,7 @@ int launch_dequant_batch(const DequantBatch& batch, cudaStream_t stream) {
   }
   ProfScope _ps(KK_DEQUANT, 0, bytes, stream);
   count_launch(KK_DEQUANT);
-  const unsigned grid = static_cast<unsigned>(std::min<long long>((max_units + 2047) / 2048, num_sms()));
+  const unsigned grid = static_cast<unsigned>(std::min<long long>((max_units + 2047) / 2048, 16LL * num_sms()));
   dequant_batch_kernel<<<grid, 256, 0, stream>>>(batch);
   FB_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -295,8 +295,15 @@ int fluxb200_clip_forward(fluxb200_clip* m, const int32_t* ids, void* hidden_out
  *   "qkrope_fusion"  QK-norm + RoPE fused into the q|k|v GEMM epilogue (default 1)
  *   "gemm_pair"      cta_group::2 GEMM (default 1; FLUXB200_GEMM_SINGLE_CTA=1 turns it off)
  *   "gemm_cl4"       cluster-of-4 GEMM with W multicast (default 0: measured slower; FLUXB200_GEMM_CL4=1)
- *   "fused_dequant"  model path: quantised weights expanded inside the GEMM's operand producer instead of through an
- *                    L2-sized bf16 staging buffer (default 0: at M = 4608 tokens per weight the staged path is faster)
+ *   "dequant_mode"   how a quantised model weight reaches the tensor cores (FLUXB200_DEQUANT_MODE=n); same bits in all:
+ *                      0 (default) fluxb200_model_denoise expands every quantised weight ONCE per call into a bf16 cache
+ *                        carved from the caller's workspace (+2 B per quantised weight: 23.8 GB for a fully quantised
+ *                        FLUX.1-dev, nothing on a 180 GB part) and every step runs dense GEMMs; the resident model stays
+ *                        packed.  A single fluxb200_model_forward has no image to amortise over and behaves like 1.
+ *                      1 staged per layer: each step expands each weight into an L2-sized staging buffer before its
+ *                        GEMM, one weight ahead on a side stream ("dequant_overlap")
+ *                      2 fused: the GEMM's producer warps expand the packed tile in shared memory (no bf16 copy in HBM)
+ *   "fused_dequant"  older name: 1 = dequant_mode 2, 0 = dequant_mode 0
  *   "attn_variant"   build of the attention kernel, see attention.cu (default 0; FLUXB200_ATTN_VARIANT=n)
  *   "pdl"            programmatic dependent launch for GEMM / attention / LN-modulate (default 1; FLUXB200_PDL=0)
  *   "step_graph"     fluxb200_model_denoise replays one captured CUDA graph per step (default 1; FLUXB200_STEP_GRAPH=0)

@@ -43,6 +43,11 @@ for M, N, K in [(4608, 3072, 3072), (4096, 9216, 3072), (4608, 21504, 3072), (40
     fl = 2 * M * N * K
     res.append(dict(kind="gemm", M=M, N=N, K=K, ms=ms, tflops=fl / ms / 1e9, cublas_ms=ms_t, cublas_tflops=fl / ms_t / 1e9))
     print(res[-1], flush=True)
+    if K >= 12288 or (M, N, K) == (4608, 3072, 3072):  # the shapes that run with the gate * x + residual epilogue (in place)
+        gate = torch.randn(1, N, device="cuda").bfloat16()
+        ms = timeit(lambda: ops.linear(x, w, b, gate=gate, rows_per_batch=M, res=out, out=out))
+        res.append(dict(kind="gemm+gate+res", M=M, N=N, K=K, ms=ms, tflops=fl / ms / 1e9))
+        print(res[-1], flush=True)
     if (M, N, K) == (4096, 12288, 3072):
         ms = timeit(lambda: ops.linear(x, w, b, act=ops.ACT_GELU, out=out))
         res.append(dict(kind="gemm+gelu", M=M, N=N, K=K, ms=ms, tflops=fl / ms / 1e9))

@@ -278,18 +278,23 @@ def test_quantised_dit_step(fluxlib, kind, geom):
     torch.cuda.synchronize()
     assert torch.equal(out, out_staged), "fused and staged de-quantisation must feed identical bf16 weights to the MMA"
     assert torch.equal(out_staged, out_inorder), "side-stream expansion pipeline changed the result"
-    if geom[0] == 8:  # the denoising loop (CUDA graph with the expansion branch captured) == eager single steps + Euler
+    if geom[0] == 8:
+        # the denoising loop in all three weight modes (0: per-image bf16 cache in the workspace, 1: staged per layer
+        # with the expansion branch captured in the step graph, 2: fused producer) == eager single steps + Euler
         ts = OF.get_timesteps(3, OF.calculate_shift(16))
-        x = args[0].clone()
-        m.denoise(x, args[1], args[2], args[3], args[5], 3.5, ts)
-        used, note = m.denoise_info()
-        assert used, note
         xr = args[0].clone()
         for tc, tp in zip(ts[:-1], ts[1:]):
             pred = m.forward(xr, args[1], args[2], args[3], torch.tensor([tc], dtype=torch.float32), args[5], gd)
             xr = xr + pred * torch.tensor(float(tp - tc)).to(torch.bfloat16)
-        torch.cuda.synchronize()
-        assert torch.equal(x, xr)
+        for mode in (0, 1, 2):
+            L.check(fluxlib.fluxb200_set_flag(b"dequant_mode", mode))
+            x = args[0].clone()
+            m.denoise(x, args[1], args[2], args[3], args[5], 3.5, ts)
+            used, note = m.denoise_info()
+            torch.cuda.synchronize()
+            assert used, note
+            assert torch.equal(x, xr), f"dequant_mode {mode}"
+        L.check(fluxlib.fluxb200_set_flag(b"dequant_mode", 0))
 
     class QOracle(OF.FluxOracle):
         def lin3(self, x, name):
