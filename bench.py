@@ -298,9 +298,13 @@ def run_ours(args):
         ms = a.elapsed_time(b)
         if world > 1:
             t = torch.tensor([ms], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = t.item()
+            every = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(every, t)
+            rank_ms[fn.__name__] = [round(x.item() / k, 2) for x in every]  # per-rank ms per step: the spread is hardware
+            ms = max(x.item() for x in every)
         return ms
+
+    rank_ms = {}
 
     # ---- warm-up ----
     for _ in range(args.warmup):
@@ -413,6 +417,8 @@ def run_ours(args):
     }
     line["dit_ms_per_step"] = (ms_total / args.steps) / params.num_steps  # upper bound: includes the VAE share
     line["profiled_image_ms"] = ms_prof
+    if rank_ms:  # value = max over ranks (slowest GPU of the box); the per-rank figures show how far the others are ahead
+        line["ms_per_step_by_rank"] = rank_ms
     if clocks and clocks.get("power_w"):  # the loop is power-capped: energy per image is what kernel variants trade
         line["joules_per_image_per_gpu"] = clocks["power_w"] * (ms_total / args.steps / 1e3) / B
     graph_used, graph_note = pipe.transformer.denoise_info()

@@ -29,6 +29,8 @@ NVCC_FLAGS = [
 def _flags() -> list[str]:
     """NVCC_FLAGS plus opt-in debug instrumentation (FLUXB200_GEMM_TRACE=1: clock64 trace of the GEMM's MMA thread)."""
     extra = ["-DFB_GEMM_TRACE=1"] if os.environ.get("FLUXB200_GEMM_TRACE") == "1" else []
+    if os.environ.get("FLUXB200_FULL_WAIT_CLUSTER") == "1":  # A/B build: round-1 cluster-scope wait in the GEMM main loop
+        extra.append("-DFB_FULL_WAIT_CLUSTER=1")
     return NVCC_FLAGS + extra
 
 

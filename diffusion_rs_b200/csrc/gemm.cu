@@ -26,6 +26,9 @@
 #ifndef FB_GEMM_TRACE
 #define FB_GEMM_TRACE 0
 #endif
+#ifndef FB_FULL_WAIT_CLUSTER
+#define FB_FULL_WAIT_CLUSTER 0  // 1: round-1 behaviour (acquire.cluster wait on the stage-full barrier), for A/B builds
+#endif
 
 namespace fb {
 
@@ -777,7 +780,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
             mbar_wait(&full_bar[stage], phase);
             mbar_wait_cluster(&peer_full[stage], phase);
           } else if (CTA2) {
-            mbar_wait_cluster(&full_bar[stage], phase);
+            // CTA-scope wait: the stage was written by TMA (async proxy, both CTAs' bytes credited to this barrier) and
+            // is read by tcgen05.mma (async proxy); the barrier's completion orders the two.  An acquire.cluster
+            // try_wait is a cluster-scope fence on EVERY k-block and showed up as "MMA thread waits for TMA data".
+            if (FB_FULL_WAIT_CLUSTER) mbar_wait_cluster(&full_bar[stage], phase); else mbar_wait(&full_bar[stage], phase);
           } else {
             mbar_wait(&full_bar[stage], phase);
           }
@@ -984,7 +990,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_big_kernel(const
         int acc0 = 0;
         if (it.nsub == 2) small_count = 0; else acc0 = small_count++ & 1;
         for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait_cluster(&full_bar[stage], phase);
+          if (FB_FULL_WAIT_CLUSTER) mbar_wait_cluster(&full_bar[stage], phase); else mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
           const uint64_t db = umma_smem_desc_sw128(sa + 2 * A_BYTES, 16, 1024);

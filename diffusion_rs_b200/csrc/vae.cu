@@ -121,22 +121,42 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ 
   const int cv = C / 8;
   const int vec = static_cast<int>(i % cv);
   const long long off = (static_cast<long long>(n) * vec_per_image + i) * 8;
-  float f[8], wf[8], bfv[8], o[8];
-  unpack8v(*reinterpret_cast<const uint4*>(x + off), f);
-  unpack8v(*reinterpret_cast<const uint4*>(w + vec * 8), wf);
-  unpack8v(*reinterpret_cast<const uint4*>(b + vec * 8), bfv);
   const float2 st0 = gs[(vec * 8) / cpg], st1 = gs[(vec * 8 + 4) / cpg];
+  // The kernel was instruction-bound (1.1-1.3 TB/s: two f32 divisions and an expf per element).  Now: the division by
+  // sqrt(var + eps) is a reciprocal + one Newton step (correctly rounded quotient, 3 FMAs); * w and + b run as packed
+  // bf16x2 ops (an HMUL2/HADD2.BF16 is exactly "f32 op, round to nearest even", the reference's per-op rounding); SiLU
+  // keeps its three bf16 roundings with ex2.approx / a Newton-corrected reciprocal in f32.
+  const float inv0 = 1.0f / st0.y, inv1 = 1.0f / st1.y;
+  const uint4 xu = *reinterpret_cast<const uint4*>(x + off);
+  const uint4 wu = *reinterpret_cast<const uint4*>(w + vec * 8);
+  const uint4 bu = *reinterpret_cast<const uint4*>(b + vec * 8);
+  const uint32_t xw[4] = {xu.x, xu.y, xu.z, xu.w}, ww[4] = {wu.x, wu.y, wu.z, wu.w}, bw[4] = {bu.x, bu.y, bu.z, bu.w};
+  uint32_t ow[4];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const float2 st = e < 4 ? st0 : st1;
-    const float nx = rbf((f[e] - st.x) / st.y);
-    float v = rbf(rbf(nx * wf[e]) + bfv[e]);
-    if (apply_silu) v = silu_steps(v);
-    o[e] = v;
+  for (int e = 0; e < 4; ++e) {
+    const float mean = e < 2 ? st0.x : st1.x, den = e < 2 ? st0.y : st1.y, inv = e < 2 ? inv0 : inv1;
+    const float d0 = bf_lo(xw[e]) - mean, d1 = bf_hi(xw[e]) - mean;
+    float q0 = d0 * inv, q1 = d1 * inv;
+    q0 = fmaf(fmaf(-q0, den, d0), inv, q0);
+    q1 = fmaf(fmaf(-q1, den, d1), inv, q1);
+    __nv_bfloat162 v = __floats2bfloat162_rn(q0, q1);                                          // normalised -> bf16
+    v = __hmul2_rn(v, *reinterpret_cast<const __nv_bfloat162*>(&ww[e]));                       // * w -> bf16
+    v = __hadd2_rn(v, *reinterpret_cast<const __nv_bfloat162*>(&bw[e]));                       // + b -> bf16
+    if (apply_silu) {  // v / (1 + exp(-v)), every op rounded to bf16 (core/op.rs:703-705)
+      const float2 f = __bfloat1622float2(v);
+      const __nv_bfloat162 en = __floats2bfloat162_rn(ex2_approx(-f.x * 1.4426950408889634f),
+                                                      ex2_approx(-f.y * 1.4426950408889634f));
+      const float2 dd = __bfloat1622float2(__hadd2_rn(en, __float2bfloat162_rn(1.0f)));
+      float r0 = __frcp_rn(dd.x), r1 = __frcp_rn(dd.y);
+      float s0 = f.x * r0, s1 = f.y * r1;
+      // exp(-v) overflows to inf for v < -88.7: v / inf = -0, and the Newton step would turn it into 0 * inf = NaN
+      s0 = dd.x > 3.0e38f ? f.x * 0.0f : fmaf(fmaf(-s0, dd.x, f.x), r0, s0);
+      s1 = dd.y > 3.0e38f ? f.y * 0.0f : fmaf(fmaf(-s1, dd.y, f.y), r1, s1);
+      v = __floats2bfloat162_rn(s0, s1);
+    }
+    ow[e] = *reinterpret_cast<const uint32_t*>(&v);
   }
-  uint4 u;
-  u.x = pack_bf16(o[0], o[1]), u.y = pack_bf16(o[2], o[3]), u.z = pack_bf16(o[4], o[5]), u.w = pack_bf16(o[6], o[7]);
-  *reinterpret_cast<uint4*>(y + off) = u;
+  *reinterpret_cast<uint4*>(y + off) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
 }
 
 int launch_groupnorm_silu(const bf16* x, const bf16* w, const bf16* b, bf16* y, int N, int HW, int C, int groups,
