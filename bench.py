@@ -374,9 +374,11 @@ def run_ours(args):
     if gemm.get("launches"):
         ach = gemm["flops"] / (gemm["ms"] / 1e3) / 1e12
         traffic = None
-        tj = ROOT / "profiles" / "r1b_gemm_traffic.json"  # ncu --set full capture of this launch shape (profiles/)
-        if tj.exists():
-            traffic = json.loads(tj.read_text()).get("dram_bytes_per_launch")
+        for name in ("r2_gemm_traffic.json", "r1b_gemm_traffic.json"):  # ncu --set full capture of this launch shape
+            tj = ROOT / "profiles" / name
+            if tj.exists():
+                traffic = json.loads(tj.read_text()).get("dram_bytes_per_launch")
+                break
         roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel", "achieved": ach,
                     "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tflops_sustained"],
                     "traffic": traffic,
