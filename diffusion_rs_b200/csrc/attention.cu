@@ -417,24 +417,41 @@ __global__ void __launch_bounds__((COOP ? 12 : 8 * RPT + 4) * 32, 1) attention_t
         tc_fence_after();
         if (TRACE && tr && j < 64) tr[(j * 2 + g) * 8 + 0] = clock64();
         uint32_t s[COLS];
-#pragma unroll
-        for (int c = 0; c < COLS / 32; ++c) tmem_ld32(tS + c * 32, &s[c * 32]);
-        tc_wait_ld();
-        if (TRACE && tr && j < 64) tr[(j * 2 + g) * 8 + 1] = clock64();
         const int kv_valid = P.L - j * TKV - h * COLS;  // valid columns among mine; >= COLS except on the last block
-        if (kv_valid < COLS) {
-#pragma unroll
-          for (int i = 0; i < COLS; ++i)
-            if (i >= kv_valid) s[i] = __float_as_uint(-INFINITY);
-        }
         // row max over my columns: four independent 3-input max chains
         float bm0 = -INFINITY, bm1 = -INFINITY, bm2 = -INFINITY, bm3 = -INFINITY;
+        auto max_over = [&](int i0, int i1) {
 #pragma unroll
-        for (int i = 0; i < COLS; i += 8) {
-          bm0 = fmax3(bm0, __uint_as_float(s[i + 0]), __uint_as_float(s[i + 1]));
-          bm1 = fmax3(bm1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
-          bm2 = fmax3(bm2, __uint_as_float(s[i + 4]), __uint_as_float(s[i + 5]));
-          bm3 = fmax3(bm3, __uint_as_float(s[i + 6]), __uint_as_float(s[i + 7]));
+          for (int i = i0; i < i1; i += 8) {
+            bm0 = fmax3(bm0, __uint_as_float(s[i + 0]), __uint_as_float(s[i + 1]));
+            bm1 = fmax3(bm1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
+            bm2 = fmax3(bm2, __uint_as_float(s[i + 4]), __uint_as_float(s[i + 5]));
+            bm3 = fmax3(bm3, __uint_as_float(s[i + 6]), __uint_as_float(s[i + 7]));
+          }
+        };
+        if (COLS == 128 && kv_valid >= COLS) {
+          // the TMEM read of a 128-column row is the long pole of this phase: scan the first half for its maximum while
+          // the second half is still in flight
+          tmem_ld32(tS, &s[0]);
+          tmem_ld32(tS + 32, &s[32]);
+          tc_wait_ld();
+          tmem_ld32(tS + 64, &s[COLS / 2]);
+          tmem_ld32(tS + 96, &s[COLS / 2 + 32 < COLS ? COLS / 2 + 32 : 0]);
+          max_over(0, COLS / 2);
+          tc_wait_ld();
+          if (TRACE && tr && j < 64) tr[(j * 2 + g) * 8 + 1] = clock64();
+          max_over(COLS / 2, COLS);
+        } else {
+#pragma unroll
+          for (int c = 0; c < COLS / 32; ++c) tmem_ld32(tS + c * 32, &s[c * 32]);
+          tc_wait_ld();
+          if (TRACE && tr && j < 64) tr[(j * 2 + g) * 8 + 1] = clock64();
+          if (kv_valid < COLS) {
+#pragma unroll
+            for (int i = 0; i < COLS; ++i)
+              if (i >= kv_valid) s[i] = __float_as_uint(-INFINITY);
+          }
+          max_over(0, COLS);
         }
         float bmax = fmaxf(fmaxf(bm0, bm1), fmaxf(bm2, bm3));
         if (RPT == 2) {  // both threads of the row must use the same reference

@@ -983,22 +983,34 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_big_kernel(const
       uint32_t phase = 0;
       uint32_t acc_phase = 0;  // bit a: phase of accumulator a
       int small_count = 0;
+#if FB_GEMM_TRACE
+      long long* const trace = (unit_id == 0) ? P.trace : nullptr;
+#else
+      constexpr long long* trace = nullptr;
+#endif
+      int item_no = 0;
       for (int w = unit_id; w < P.total_items; w += num_units) {
         const BigItem it = decode_big_item(P, w);
         if (it.nsub == 0) continue;
         const GemmProblemDev& p = P.p[it.prob];
         int acc0 = 0;
         if (it.nsub == 2) small_count = 0; else acc0 = small_count++ & 1;
+        const long long c0 = trace ? clock64() : 0;
+        long long full_wait = 0, acc_wait = 0;
         for (int kb = 0; kb < p.num_kb; ++kb) {
+          const long long w0 = trace ? clock64() : 0;
           if (FB_FULL_WAIT_CLUSTER) mbar_wait_cluster(&full_bar[stage], phase); else mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          if (trace) full_wait += clock64() - w0;
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
           const uint64_t db = umma_smem_desc_sw128(sa + 2 * A_BYTES, 16, 1024);
           for (int s = 0; s < it.nsub; ++s) {
             const int acc = acc0 + s;
             if (kb == 0) {  // the epilogue (of both CTAs) must have drained this accumulator
+              const long long a0 = trace ? clock64() : 0;
               mbar_wait_cluster(&tmem_empty[acc], ((acc_phase >> acc) & 1u) ^ 1u);
               tc_fence_after();
+              if (trace) acc_wait += clock64() - a0;
             }
             const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
             const uint64_t da = umma_smem_desc_sw128(sa + s * A_BYTES, 16, 1024);
@@ -1015,6 +1027,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_big_kernel(const
             phase ^= 1;
           }
         }
+        if (trace && item_no < 64) {
+          trace[item_no * 4 + 0] = c0;                      // item start
+          trace[item_no * 4 + 1] = acc_wait;                // waited for the epilogue to free the accumulator(s)
+          trace[item_no * 4 + 2] = full_wait;               // waited for TMA data, summed over the k-blocks
+          trace[item_no * 4 + 3] = (clock64() - c0) * 4 + it.nsub;  // item total (issue side) x4 + sub-tile count
+        }
+        ++item_no;
       }
     }
   } else {

@@ -16,8 +16,9 @@ from diffusion_rs_b200 import build, lib as L, ops  # noqa: E402
 build.build()
 lib = L.load()
 trace = torch.zeros(64 * 4, dtype=torch.int64, device="cuda")
-shapes = [(4608, 21504, 3072, "plain"), (4608, 3072, 15360, "plain"), (4608, 12288, 3072, "gelu"), (4608, 3072, 3072, "gate"),
-          (4608, 9216, 3072, "plain"), (8192, 8192, 8192, "plain")]
+BIG = int(os.environ.get("FLUXB200_GEMM_BIG", "0"))
+shapes = [(4608, 3072, 15360, "plain"), (4096, 3072, 12288, "gate"), (4608, 21504, 3072, "plain"), (4608, 3072, 3072, "gate"),
+          (8192, 8192, 8192, "plain")]
 for M, N, K, mode in shapes:
     x = torch.randn(M, K, device="cuda").bfloat16()
     w = (torch.randn(N, K, device="cuda") / math.sqrt(K)).bfloat16()
@@ -44,10 +45,17 @@ for M, N, K, mode in shapes:
     e.record()
     torch.cuda.synchronize()
     L.check(lib.fluxb200_debug_gemm_trace(None))
-    t = trace.cpu().view(64, 4)
+    t = trace.cpu().view(64, 4).clone()
     n = int((t[:, 3] > 0).sum())
     t = t[:n]
     kb = K // 64
+    if BIG and (BIG >= 2 or K >= 8192):  # the 512x256 kernel packs (item total x 4 + sub-tile count) into field 3
+        nsub = t[:, 3] % 4
+        t[:, 3] //= 4
+        rows = [(int(nsub[i]), int(t[i, 1]), int(t[i, 2]), int(t[i, 3]), kb * 4 * 128 * int(nsub[i])) for i in range(n)]
+        print(f"{M}x{N}x{K} {mode} BIG: {a.elapsed_time(e)*1e3:.1f} us, {2*M*N*K/a.elapsed_time(e)/1e9:.0f} TFLOP/s; unit 0 items "
+              f"(sub-tiles, wait accumulator, wait TMA, total, MMA floor): {rows}")
+        continue
     floor = kb * 4 * 128
     ms = a.elapsed_time(e)
     span = int(t[-1, 0] + t[-1, 3] - t[0, 0])
