@@ -76,6 +76,7 @@ struct alignas(64) GemmProblemDev {
   CUtensorMap tmap_b4;  // CL4: 64-row boxes of W
   int M, N, K, num_kb;
   int tiles_m, tiles_n, tile_begin, tile_end;
+  int real_tiles_n;  // BIG kernel, N-direction: tiles_n counts 512-column positions, this is the number of 256-column tiles
   int sched_m;  // scheduling units along M: tiles_m (single CTA), ceil(tiles_m / 2) (CTA pair), ceil(tiles_m / 4) (CL4)
   int group_m;  // rasterisation: tiles are walked M-fastest inside groups of `group_m` M-units
   int conv, cH, cW, cC, c_chunks, ksize, tiles_h, tiles_w;
@@ -113,6 +114,7 @@ struct GemmParams {
   // BIG kernel: tile_begin / sched_m of the problems count 512-row "positions"; the first n_big positions are computed
   // as 512x256 tiles, the remaining ones as their two 256x256 halves; total_items = n_big + 2 * (positions - n_big)
   int n_big, total_items;
+  int big_ndir;  // BIG kernel: 0 = the two sub-tiles of an item are stacked along M (share W); 1 = side by side along N (share A)
   long long* trace;  // debug (fluxb200_debug_gemm_trace): per tile of scheduling unit 0, clock64 waits of the MMA thread
 };
 
@@ -882,8 +884,8 @@ struct BigCfg {
 };
 
 struct BigItem {
-  int prob, n_t, nsub;  // nsub = 0: nothing to do (second half of an odd M edge)
-  int blk0;             // first 256-row block of the item; sub-tile s covers block blk0 + s
+  int prob, nsub;      // nsub = 0: nothing to do (second half of an odd edge)
+  int blk[2], nt[2];   // sub-tile s = 256-row block blk[s] x 256-column tile nt[s]
 };
 
 __device__ __forceinline__ BigItem decode_big_item(const GemmParams& P, int w) {
@@ -896,14 +898,25 @@ __device__ __forceinline__ BigItem decode_big_item(const GemmParams& P, int w) {
   }
   const TileCoord tc = decode_tile(P, pos);
   const GemmProblemDev& p = P.p[tc.prob];
-  const int blocks = (p.tiles_m + 1) / 2;  // 256-row blocks of the problem
-  const bool have2 = 2 * tc.m_t + 1 < blocks;
   BigItem it;
-  it.prob = tc.prob, it.n_t = tc.n_t;
-  if (sub_sel < 0) {
-    it.blk0 = 2 * tc.m_t, it.nsub = have2 ? 2 : 1;
+  it.prob = tc.prob;
+  int first, count;  // index of the item's first sub-tile along the doubled direction, number of sub-tiles there
+  if (P.big_ndir) {
+    first = 2 * tc.n_t, count = p.real_tiles_n;
   } else {
-    it.blk0 = 2 * tc.m_t + sub_sel, it.nsub = (sub_sel == 0 || have2) ? 1 : 0;
+    first = 2 * tc.m_t, count = (p.tiles_m + 1) / 2;  // 256-row blocks of the problem
+  }
+  const bool have2 = first + 1 < count;
+  int i0;
+  if (sub_sel < 0) {
+    i0 = first, it.nsub = have2 ? 2 : 1;
+  } else {
+    i0 = first + sub_sel, it.nsub = (sub_sel == 0 || have2) ? 1 : 0;
+  }
+  if (P.big_ndir) {
+    it.blk[0] = it.blk[1] = tc.m_t, it.nt[0] = i0, it.nt[1] = i0 + 1;
+  } else {
+    it.blk[0] = i0, it.blk[1] = i0 + 1, it.nt[0] = it.nt[1] = tc.n_t;
   }
   return it;
 }
@@ -958,16 +971,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_big_kernel(const
         const BigItem it = decode_big_item(P, w);
         if (it.nsub == 0) continue;
         const GemmProblemDev& p = P.p[it.prob];
-        const int b_row0 = it.n_t * BLOCK_N + static_cast<int>(cta_rank) * (BLOCK_N / 2);
+        const bool nd = P.big_ndir != 0;
+        // stage = three 16 KB slots: M direction [A sub 0][A sub 1][W]; N direction [A][W sub 0][W sub 1]
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * STAGE_BYTES;
           const uint32_t bar = bar_base + stage * 8;
           if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (it.nsub * A_BYTES + BigCfg::B_BYTES));
-          for (int s = 0; s < it.nsub; ++s)
+          for (int s = 0; s < (nd ? 1 : it.nsub); ++s)
             tma_load_2d_2sm(sa + s * A_BYTES, &p.tmap_a, bar, kb * BLOCK_K,
-                            (2 * (it.blk0 + s) + static_cast<int>(cta_rank)) * BLOCK_M);
-          tma_load_2d_2sm(sa + 2 * A_BYTES, &p.tmap_b, bar, kb * BLOCK_K, b_row0);
+                            (2 * it.blk[s] + static_cast<int>(cta_rank)) * BLOCK_M);
+          for (int s = 0; s < (nd ? it.nsub : 1); ++s)
+            tma_load_2d_2sm(sa + (nd ? 1 + s : 2) * A_BYTES, &p.tmap_b, bar, kb * BLOCK_K,
+                            it.nt[s] * BLOCK_N + static_cast<int>(cta_rank) * (BLOCK_N / 2));
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -1003,7 +1019,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_big_kernel(const
           tc_fence_after();
           if (trace) full_wait += clock64() - w0;
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-          const uint64_t db = umma_smem_desc_sw128(sa + 2 * A_BYTES, 16, 1024);
+          const bool nd = P.big_ndir != 0;
           for (int s = 0; s < it.nsub; ++s) {
             const int acc = acc0 + s;
             if (kb == 0) {  // the epilogue (of both CTAs) must have drained this accumulator
@@ -1013,7 +1029,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_big_kernel(const
               if (trace) acc_wait += clock64() - a0;
             }
             const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-            const uint64_t da = umma_smem_desc_sw128(sa + s * A_BYTES, 16, 1024);
+            const uint64_t da = umma_smem_desc_sw128(sa + (nd ? 0 : s) * A_BYTES, 16, 1024);
+            const uint64_t db = umma_smem_desc_sw128(sa + (nd ? 1 + s : 2) * A_BYTES, 16, 1024);
 #pragma unroll
             for (int k = 0; k < BLOCK_K / 16; ++k) umma_ss_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
             if (kb == p.num_kb - 1) {  // this accumulator is complete once the MMAs issued so far retire
@@ -1048,8 +1065,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_big_kernel(const
       if (it.nsub == 2) small_count = 0; else acc0 = small_count++ & 1;
       for (int s = 0; s < it.nsub; ++s) {
         const int acc = acc0 + s;
-        const int m_t = 2 * (it.blk0 + s) + static_cast<int>(cta_rank);
-        epi_drain<EPI_WARPS, false>(p, it.n_t, m_t, tmem_base + acc * BLOCK_N, warp, lane, &tmem_full[acc],
+        const int m_t = 2 * it.blk[s] + static_cast<int>(cta_rank);
+        epi_drain<EPI_WARPS, false>(p, it.nt[s], m_t, tmem_base + acc * BLOCK_N, warp, lane, &tmem_full[acc],
                                     (ephase >> acc) & 1u);
         tc_fence_before();
         __syncwarp();
@@ -1134,15 +1151,18 @@ int launch_gemm(const GemmDesc* descs, int count, cudaStream_t stream) {
   if (use_cl4 && max_clusters4 < 1) use_cl4 = false;
   // BIG tiles (512x256 per pair, see gemm_tcgen05_big_kernel): dense long-K problems with at least one full wave
   // ("gemm_big" = 1: K >= 8192; 2: every eligible GEMM, for experiments)
-  const int big_flag = get_flag("gemm_big");
+  const int big_flag = get_flag("gemm_big");  // 1/2: sub-tiles stacked along M (share W); 3/4: side by side along N (share A)
+  const bool big_ndir = big_flag >= 3;
+  const bool big_all = big_flag == 2 || big_flag == 4;
   bool use_big = use_pair && !quant_b && !use_cl4 && big_flag > 0;
   {
     long long positions = 0;
     for (int i = 0; i < count && use_big; ++i) {
       const GemmDesc& d = descs[i];
-      if (d.conv || d.qkrope || d.K % BLOCK_K != 0 || (big_flag < 2 && d.K < 8192)) use_big = false;
-      const int blocks = (d.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
-      positions += static_cast<long long>((blocks + 1) / 2) * ((d.N + BLOCK_N - 1) / BLOCK_N);
+      if (d.conv || d.qkrope || d.n_split || d.K % BLOCK_K != 0 || (!big_all && d.K < 8192)) use_big = false;
+      const int blocks = (d.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M), ntiles = (d.N + BLOCK_N - 1) / BLOCK_N;
+      positions += big_ndir ? static_cast<long long>(blocks) * ((ntiles + 1) / 2)
+                            : static_cast<long long>((blocks + 1) / 2) * ntiles;
     }
     if (positions < num_sms() / 2) use_big = false;
   }
@@ -1232,7 +1252,9 @@ int launch_gemm(const GemmDesc* descs, int count, cudaStream_t stream) {
       }
     }
     p.tiles_n = (d.N + BLOCK_N - 1) / BLOCK_N;
-    p.sched_m = (use_cl4 || use_big) ? (p.tiles_m + 3) / 4 : (use_pair ? (p.tiles_m + 1) / 2 : p.tiles_m);
+    p.real_tiles_n = p.tiles_n;
+    p.sched_m = (use_cl4 || (use_big && !big_ndir)) ? (p.tiles_m + 3) / 4 : (use_pair ? (p.tiles_m + 1) / 2 : p.tiles_m);
+    if (use_big && big_ndir) p.tiles_n = (p.tiles_n + 1) / 2;  // positions are 256 rows x 512 columns
     // L2-aware rasterisation: when the whole A operand fits comfortably in the 126 MB L2 (activations of one DiT
     // block: 28 MB), walk all of M for a few N tiles at a time so that every weight panel is fetched from HBM once
     // (ncu: 650 MB -> ~algorithmic 360 MB of DRAM traffic for the 4608x21504x3072 launch); otherwise groups of 8.
@@ -1282,6 +1304,7 @@ int launch_gemm(const GemmDesc* descs, int count, cudaStream_t stream) {
   }
   P.total_tiles = tile;
   P.trace = g_gemm_trace;
+  P.big_ndir = big_ndir ? 1 : 0;
   if (use_big) {
     const int units = num_sms() / 2;
     P.n_big = (tile / units) * units;  // full waves of 512x256 tiles; the rest as 256x256 halves

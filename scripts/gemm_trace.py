@@ -49,7 +49,7 @@ for M, N, K, mode in shapes:
     n = int((t[:, 3] > 0).sum())
     t = t[:n]
     kb = K // 64
-    if BIG and (BIG >= 2 or K >= 8192):  # the 512x256 kernel packs (item total x 4 + sub-tile count) into field 3
+    if BIG and (BIG in (2, 4) or K >= 8192):  # the 512x256 kernel packs (item total x 4 + sub-tile count) into field 3
         nsub = t[:, 3] % 4
         t[:, 3] //= 4
         rows = [(int(nsub[i]), int(t[i, 1]), int(t[i, 2]), int(t[i, 3]), kb * 4 * 128 * int(nsub[i])) for i in range(n)]

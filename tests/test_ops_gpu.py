@@ -43,9 +43,11 @@ def test_linear_plain(fluxlib, M, N, K):
 
 
 @pytest.mark.parametrize("M,N,K,flag", [(4608, 3072, 12288, 1), (4112, 3072, 8192, 1), (4608, 3072, 15360, 1),
-                                        (2500, 12288, 3072, 2)])
+                                        (2500, 12288, 3072, 2), (4608, 3072, 12288, 3), (4112, 3328, 8192, 3),
+                                        (2500, 12288, 3072, 4)])
 def test_linear_big_tiles_bit_identical(fluxlib, M, N, K, flag):
-    """The 512x256-per-CTA-pair kernel for the long-K GEMMs (hybrid work list: full waves of big tiles + 256x256 halves)
+    """flag 1/2: 512x256 items (two sub-tiles stacked along M share W), 3/4: 256x512 items (side by side along N, share A;
+    3328 columns = 13 tiles: odd edge).  The 512x256-per-CTA-pair kernel for the long-K GEMMs (hybrid work list: full waves of big tiles + 256x256 halves)
     accumulates every output element over k in the same order as the 256x256 kernel: same bits, including the fused
     gate * x + residual epilogue and ragged / odd M edges (4112 rows = 33 tiles of 128)."""
     from diffusion_rs_b200 import lib as L
@@ -59,14 +61,14 @@ def test_linear_big_tiles_bit_identical(fluxlib, M, N, K, flag):
     outs = []
     for f in (0, flag):
         L.check(fluxlib.fluxb200_set_flag(b"gemm_big", f))
-        if flag == 2:
+        if flag in (2, 4):
             outs.append(ops.linear(x, w, b, bias_mode=ops.BIAS_FUSED, act=ops.ACT_GELU))
         else:
             outs.append(ops.linear(x, w, b, bias_mode=ops.BIAS_FUSED, gate=gate, rows_per_batch=rpb, res=res))
     L.check(fluxlib.fluxb200_set_flag(b"gemm_big", 0))
     torch.cuda.synchronize()
     assert torch.equal(outs[0], outs[1])
-    if flag == 1 and M == 4112:  # and the result is right, not just equal
+    if flag in (1, 3) and M == 4112:  # and the result is right, not just equal
         b_idx = (torch.arange(M, device="cuda") // rpb)
         ref = O.rb(res.float() + O.rb(gate.float()[b_idx] * O.linear(x.float(), w.float(), b.float(), fused_bias=True)))
         assert _err(outs[1], ref)[1] < 2e-3
