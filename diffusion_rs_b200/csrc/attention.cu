@@ -581,6 +581,9 @@ static const AttnVariant kAttnVariants[] = {
     FB_ATTN_VARIANT_COOP(false, 0x88, "1 CTA, 8 softmax warps serve both tiles (half a row per thread), poly 1/4"),
     FB_ATTN_VARIANT_COOP(false, 0, "1 CTA, cooperative softmax warps, all exp2 on the MUFU"),
     FB_ATTN_VARIANT_COOP(true, 0x88, "CTA pair, cooperative softmax warps, poly 1/4"),
+    FB_ATTN_VARIANT(false, 0x88, 1, false, 1, "1 CTA, poly 1/4, no MUFU ping-pong"),
+    FB_ATTN_VARIANT(false, 0x08, 1, true, 1, "1 CTA, poly 1/8, ping-pong"),
+    FB_ATTN_VARIANT(false, 0x08, 1, false, 1, "1 CTA, poly 1/8, no MUFU ping-pong"),
 };
 static constexpr int kNumAttnVariants = sizeof(kAttnVariants) / sizeof(kAttnVariants[0]);
 
