@@ -79,7 +79,7 @@ ProfScope::~ProfScope() {
 }
 
 static int g_flag_qkrope = 1, g_flag_pair = -1, g_flag_dqm = -1, g_flag_attn = -1, g_flag_pdl = -1, g_flag_cl4 = -1,
-           g_flag_graph = -1, g_flag_big = -1, g_flag_dqo = -1;
+           g_flag_graph = -1, g_flag_big = -1, g_flag_dqo = -1, g_flag_lnr = -1;
 int get_flag(const char* name) {
   if (!strcmp(name, "qkrope_fusion")) return g_flag_qkrope;
   if (!strcmp(name, "dequant_mode")) {
@@ -104,6 +104,13 @@ int get_flag(const char* name) {
       g_flag_graph = (e && e[0] == '0') ? 0 : 1;
     }
     return g_flag_graph;
+  }
+  if (!strcmp(name, "ln_reread")) {
+    if (g_flag_lnr < 0) {
+      const char* e = getenv("FLUXB200_LN_REREAD");
+      g_flag_lnr = e ? (e[0] != '0') : 0;
+    }
+    return g_flag_lnr;
   }
   if (!strcmp(name, "dequant_overlap")) {
     if (g_flag_dqo < 0) {
@@ -261,6 +268,7 @@ int fluxb200_set_flag(const char* name, int value) {
   if (!strcmp(name, "step_graph")) { fb::g_flag_graph = value ? 1 : 0; return 0; }
   if (!strcmp(name, "gemm_big")) { fb::g_flag_big = value; return 0; }
   if (!strcmp(name, "dequant_overlap")) { fb::g_flag_dqo = value ? 1 : 0; return 0; }
+  if (!strcmp(name, "ln_reread")) { fb::g_flag_lnr = value ? 1 : 0; return 0; }
   return fb::fail(std::string("set_flag: unknown flag ") + name);
 }
 void fluxb200_profile_enable(int on) {

@@ -53,8 +53,10 @@ struct LnParams {
 // One warp per row, the row stays in registers between the two passes; a warp walks rows with the stride of the whole
 // grid, which is sized to exactly fill the machine (4 blocks of 4 warps per SM): 4608 rows over 2368 warps is two
 // balanced rounds, where one row per warp left a 15 %-full second wave.
-template <int D>
-__global__ void __launch_bounds__(128, 4) ln_modulate_kernel(const __grid_constant__ LnParams P) {
+// REREAD: the row is NOT kept in registers between the two passes but read again (it sits in L1: 32 warps x 6 KB per SM),
+// which halves the register footprint and doubles the warps in flight per SM (8 blocks instead of 4).
+template <int D, bool REREAD>
+__global__ void __launch_bounds__(128, REREAD ? 8 : 4) ln_modulate_kernel(const __grid_constant__ LnParams P) {
   constexpr int VEC = D / 256;  // uint4 (8 bf16) per lane
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   pdl_launch_dependents();
@@ -69,16 +71,19 @@ __global__ void __launch_bounds__(128, 4) ln_modulate_kernel(const __grid_consta
     const int b = lr / sg.rows_per_batch;
     const int i = lr - b * sg.rows_per_batch;
     const bf16* xr = sg.x + (static_cast<long long>(b) * sg.in_bstride_rows + sg.in_row_off + i) * D;
-    uint4 u[VEC];  // the row stays packed in registers (48 regs)
+    uint4 u[REREAD ? 1 : VEC];  // !REREAD: the row stays packed in registers (48 regs)
+    if (!REREAD) {
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) u[k] = *reinterpret_cast<const uint4*>(xr + (k * 32 + lane) * 8);
+      for (int k = 0; k < VEC; ++k) u[k] = *reinterpret_cast<const uint4*>(xr + (k * 32 + lane) * 8);
+    }
     // The kernel was instruction-bound (~15 instructions per element), not memory-bound: both passes run on packed
     // pairs - f32x2 add/fma for the statistics and the normalisation, then the modulate chain in bf16x2 (an
     // HMUL2/HADD2.BF16 is exactly "f32 op, round to nearest even", the reference's per-op rounding).
     float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
 #pragma unroll
     for (int k = 0; k < VEC; ++k) {
-      const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+      const uint4 uk = REREAD ? *reinterpret_cast<const uint4*>(xr + (k * 32 + lane) * 8) : u[REREAD ? 0 : k];
+      const uint32_t w[4] = {uk.x, uk.y, uk.z, uk.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float lo = bf_lo(w[e]), hi = bf_hi(w[e]);
@@ -107,7 +112,8 @@ __global__ void __launch_bounds__(128, 4) ln_modulate_kernel(const __grid_consta
       const int c = (k * 32 + lane) * 8;
       const uint4 fs = *reinterpret_cast<const uint4*>(sh + c);
       const uint4 fc = *reinterpret_cast<const uint4*>(sc + c);
-      const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+      const uint4 uk = REREAD ? *reinterpret_cast<const uint4*>(xr + c) : u[REREAD ? 0 : k];
+      const uint32_t w[4] = {uk.x, uk.y, uk.z, uk.w};
       const uint32_t ws[4] = {fs.x, fs.y, fs.z, fs.w};
       const uint32_t wc[4] = {fc.x, fc.y, fc.z, fc.w};
       uint32_t o[4];
@@ -147,8 +153,13 @@ int launch_ln_modulate2(const LnInput* in, int nseg, long long mod_bstride, bf16
   P.step_ptr = step_ptr, P.step_stride = step_stride;
   ProfScope _ps(KK_LN_MOD, 0, 4.0 * rows * D, stream);
   count_launch(KK_LN_MOD, 1);
-  const int grid = std::min((rows + 3) / 4, 4 * num_sms());
-  FB_CHECK_CUDA(launch_ex(ln_modulate_kernel<3072>, dim3(grid), dim3(128), 0, stream, 1, get_flag("pdl") != 0, P));
+  if (get_flag("ln_reread")) {
+    const int grid = std::min((rows + 3) / 4, 8 * num_sms());
+    FB_CHECK_CUDA(launch_ex(ln_modulate_kernel<3072, true>, dim3(grid), dim3(128), 0, stream, 1, get_flag("pdl") != 0, P));
+  } else {
+    const int grid = std::min((rows + 3) / 4, 4 * num_sms());
+    FB_CHECK_CUDA(launch_ex(ln_modulate_kernel<3072, false>, dim3(grid), dim3(128), 0, stream, 1, get_flag("pdl") != 0, P));
+  }
   FB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
