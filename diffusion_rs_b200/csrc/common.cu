@@ -108,7 +108,7 @@ int get_flag(const char* name) {
   if (!strcmp(name, "ln_reread")) {
     if (g_flag_lnr < 0) {
       const char* e = getenv("FLUXB200_LN_REREAD");
-      g_flag_lnr = e ? (e[0] != '0') : 0;
+      g_flag_lnr = e ? (e[0] != '0') : 1;
     }
     return g_flag_lnr;
   }

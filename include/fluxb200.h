@@ -309,8 +309,11 @@ int fluxb200_clip_forward(fluxb200_clip* m, const int32_t* ids, void* hidden_out
  *   "step_graph"     fluxb200_model_denoise replays one captured CUDA graph per step (default 1; FLUXB200_STEP_GRAPH=0)
  *   "dequant_overlap" staged quantised path: the expansion of the next weight runs on a side stream under the current
  *                    GEMM (default 1; FLUXB200_DEQUANT_OVERLAP=0)
+ *   "ln_reread"      ln_modulate re-reads the row from L1 in its second pass instead of keeping it in registers: half the
+ *                    registers, twice the warps per SM (default 1; FLUXB200_LN_REREAD=0); same bits
  *   "gemm_big"       512x256-per-CTA-pair tiles for the long-K GEMMs (EXPERIMENT, default 0: measured 13 % slower than
- *                    the 256x256 tiles; FLUXB200_GEMM_BIG=1, =2 for every eligible GEMM)
+ *                    the 256x256 tiles; FLUXB200_GEMM_BIG=1, =2 for every eligible GEMM; 3 / 4: the
+ *                    same with the two sub-tiles side by side along N)
  * FLUXB200_GEMM_MAX_UNITS=n limits the pair GEMM to n CTA pairs (experiments only). */
 int fluxb200_set_flag(const char* name, int value);
 void fluxb200_profile_enable(int on);
