@@ -193,11 +193,12 @@ def test_q4k_dequant(fluxlib):
     assert torch.equal(out.float().cpu(), torch.from_numpy(ref))
 
 
-def _quantize_model_weights(weights, kind):
-    """Replace every block Linear weight by its quantised form; returns (tensors, dequantised dict)."""
+def _quantize_model_weights(weights, kind, everything=False):
+    """Replace every block Linear weight (everything=True: EVERY Linear weight, incl. x_embedder / context_embedder /
+    proj_out / the embedders) by its quantised form; returns (tensors, dequantised dict)."""
     tensors, deq = {}, {}
     for name, t in weights.items():
-        is_block_linear = name.endswith(".weight") and t.dim() == 2 and ("transformer_blocks" in name)
+        is_block_linear = name.endswith(".weight") and t.dim() == 2 and (everything or "transformer_blocks" in name)
         if not is_block_linear:
             tensors[name] = t
             deq[name] = t
@@ -311,6 +312,48 @@ def test_quantised_dit_step(fluxlib, kind, geom):
     e = _rel(out, ref)
     print(f"\n{kind} DiT step L={h2 * w2 + l_txt}: rel err {e:.3e}")
     assert e < 1e-2
+
+
+def test_fully_quantised_checkpoint_falls_back_where_the_fused_producer_cannot_run(fluxlib):
+    """A bnb checkpoint that quantises EVERY Linear (the reference does: model.rs:722 builds x_embedder through `linear`
+    too): x_embedder has K = 64 (one absmax per row: the fused producer's TMA needs groups of four), proj_out has N = 64.
+    With the fused mode selected those layers must fall back to the staged expansion instead of failing at step time,
+    and the result must equal the all-staged one bit for bit."""
+    from diffusion_rs_b200 import lib as L
+    from diffusion_rs_b200.transformer import FluxConfig, FluxTransformer
+    cfg = OF.FluxConfig(num_layers=1, num_single_layers=1, guidance_embeds=True)
+    weights = OF.make_weights(cfg)
+    tensors, deq = _quantize_model_weights(weights, "nf4", everything=True)
+    m = FluxTransformer(FluxConfig(num_layers=1, num_single_layers=1, guidance_embeds=True))
+    for name, t in tensors.items():
+        m.load_weight(name, t.cuda())
+    m.finalize()
+    B, h2, w2, l_txt = 1, 8, 8, 64
+    g = torch.Generator().manual_seed(12)
+    img = torch.randn(B, h2 * w2, 64, generator=g).bfloat16()
+    txt = torch.randn(B, l_txt, 4096, generator=g).bfloat16()
+    y = torch.randn(B, 768, generator=g).bfloat16()
+    ids = OF.make_ids(h2, w2, l_txt)
+    idb = ids.bfloat16()
+    t, gd = torch.tensor([0.6]), torch.tensor([3.5])
+    args = (img.cuda(), idb[l_txt:][None].contiguous().cuda(), txt.cuda(), idb[:l_txt][None].contiguous().cuda(), t,
+            y.cuda(), gd)
+    outs = {}
+    for mode in (2, 1):
+        L.check(fluxlib.fluxb200_set_flag(b"dequant_mode", mode))
+        outs[mode] = m.forward(*args).clone()
+    L.check(fluxlib.fluxb200_set_flag(b"dequant_mode", 0))
+    torch.cuda.synchronize()
+    assert torch.equal(outs[2], outs[1])
+
+    class QOracle(OF.FluxOracle):  # every Linear is a BnbLinear: matmul -> bf16, then a separate bf16 bias add
+        def lin3(self, x, name):
+            return O.linear(x, self.w[name + ".weight"], self.w[name + ".bias"], fused_bias=False, mode=self.mode)
+
+    ref = QOracle(cfg, deq, O.REF).forward(img.float(), ids, txt.float(), t, y.float(), gd)
+    e = _rel(outs[1], ref)
+    print(f"\nfully quantised (nf4) DiT step: rel err {e:.3e}")
+    assert e < 9e-3  # measured 4.3e-3
 
 
 @pytest.mark.parametrize("kind", ["nf4", "fp4", "q4k", "int8"])
