@@ -137,6 +137,7 @@ struct Workspace {
 struct StepGraph {
   void* ws_base = nullptr;
   int B = 0, l_img = 0, l_txt = 0;
+  int steps = 0;  // the workspace layout (and with it every pointer baked into the graph) depends on the step count
   unsigned flags_sig = 0;
   cudaGraphExec_t exec = nullptr;
   unsigned long long launches[KK_COUNT] = {0};  // kernels per replay, by kind (launch accounting)
@@ -1056,16 +1057,19 @@ static unsigned flags_signature() {
 // stream — every tensor map, launch attribute (clusters, programmatic dependent launch edges) and kernel parameter
 // block is encoded at capture time — and replayed once per step; what changes from step to step is read by the
 // kernels through the device-side step counter.  Returns nullptr (with m->graph_note set) when capture is not possible.
-static StepGraph* step_graph_for(fluxb200_model* m, const Workspace& w, void* ws_base, int B, int l_img, int l_txt) {
+static StepGraph* step_graph_for(fluxb200_model* m, const Workspace& w, void* ws_base, int B, int l_img, int l_txt,
+                                 int steps) {
   const unsigned sig = flags_signature();
   for (auto& g : m->graphs)
-    if (g.ws_base == ws_base && g.B == B && g.l_img == l_img && g.l_txt == l_txt && g.flags_sig == sig) return &g;
+    if (g.ws_base == ws_base && g.B == B && g.l_img == l_img && g.l_txt == l_txt && g.steps == steps &&
+        g.flags_sig == sig)
+      return &g;
   if (m->graphs.size() >= 8) {  // bounded cache: drop the oldest capture
     if (m->graphs.front().exec) cudaGraphExecDestroy(m->graphs.front().exec);
     m->graphs.erase(m->graphs.begin());
   }
   StepGraph sg;
-  sg.ws_base = ws_base, sg.B = B, sg.l_img = l_img, sg.l_txt = l_txt, sg.flags_sig = sig;
+  sg.ws_base = ws_base, sg.B = B, sg.l_img = l_img, sg.l_txt = l_txt, sg.steps = steps, sg.flags_sig = sig;
   unsigned long long before[KK_COUNT], after[KK_COUNT];
   snapshot_launches(before);
   const int scratch_cur = m->wscratch_cur;
@@ -1174,7 +1178,7 @@ int fluxb200_model_denoise(fluxb200_model* m, void* img, const void* img_ids, co
   m->last_used_graph = 0;
   if (get_flag("step_graph") && !profiling_enabled()) {
     uint8_t* base = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(workspace), 1024));
-    sg = step_graph_for(m, w, base, batch, l_img, l_txt);
+    sg = step_graph_for(m, w, base, batch, l_img, l_txt, steps);
   }
   if (sg) {
     for (int s = 0; s < steps; ++s) {

@@ -169,6 +169,33 @@ def test_step_graph_is_bit_identical_to_eager_launches(fluxlib, small):
     assert torch.equal(outs[0], outs[2])  # second replay of the cached graph, fresh latent buffer
 
 
+def test_step_graph_cache_is_keyed_by_step_count(fluxlib, small):
+    """The workspace layout depends on the number of steps (the per-step tables come first), so a graph captured for
+    one step count must not be replayed for another one on the same workspace buffer."""
+    from diffusion_rs_b200 import lib as L
+    cfg, weights = small
+    model = _gpu_model(cfg, weights)
+    B, h2, w2, l_txt = 1, 8, 8, 64
+    img, txt, y, ids = _inputs(B, h2, w2, l_txt, cfg, seed=51)
+    ids_b = ids.to(torch.bfloat16)
+    img_ids = ids_b[l_txt:][None].contiguous().cuda()
+    txt_ids = ids_b[:l_txt][None].contiguous().cuda()
+    model.workspace(B, h2 * w2, l_txt, 9)  # one buffer, large enough for every run below
+    res = {}
+    for graph in (1, 0):
+        L.check(fluxlib.fluxb200_set_flag(b"step_graph", graph))
+        for n in (8, 3, 5, 8):
+            ts = OF.get_timesteps(n, OF.calculate_shift(16))
+            x = img.cuda().clone()
+            model.denoise(x, img_ids, txt.cuda(), txt_ids, y.cuda(), 3.5, ts)
+            torch.cuda.synchronize()
+            res.setdefault((graph, n), []).append(x.clone())
+    L.check(fluxlib.fluxb200_set_flag(b"step_graph", 1))
+    for n in (8, 3, 5):
+        for r in res[(1, n)]:
+            assert torch.equal(r, res[(0, n)][0]), f"{n} steps"
+
+
 def test_denoise_equals_forward_plus_euler(fluxlib, small):
     """The loop hoists vec_/modulations of ALL steps (M = steps*B row GEMMs) and folds the Euler update into the last
     GEMM's epilogue.  Both are row-/element-wise re-arrangements: the result must equal, bit for bit, a host loop of
