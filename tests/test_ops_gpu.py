@@ -157,6 +157,32 @@ def test_sdpa(fluxlib, B, H, L):
     assert mx < 0.05, (mx, rel)
 
 
+def test_sdpa_every_build_of_the_kernel(fluxlib):
+    """Every run-time selectable build of the attention kernel ("attn_variant": polynomial shares, hand-off instalments,
+    cooperative softmax warps, CTA pairs, ...) against the oracle on a ragged length (masked last kv block, 1000 is not a
+    multiple of 128 / 256 / 512) with a late jump of the running max."""
+    from diffusion_rs_b200 import lib as L
+    from diffusion_rs_b200 import ops
+    B, H, Lq = 1, 3, 1000
+    q = _rand((B, H, Lq, 128), 26)
+    k = _rand((B, H, Lq, 128), 27)
+    v = _rand((B, H, Lq, 128), 28)
+    k[:, :, 500:] *= 4.0
+    scale = 1.0 / math.sqrt(128)
+    ref = O.rb(O.sdpa_f32(q.float(), k.float(), v.float(), scale)).transpose(1, 2).reshape(B, Lq, H * 128)
+    n = fluxlib.fluxb200_attn_variants()
+    assert n >= 5
+    try:
+        for var in range(n):
+            L.check(fluxlib.fluxb200_set_flag(b"attn_variant", var))
+            y = ops.sdpa(q, k, v, scale)
+            torch.cuda.synchronize()
+            mx, rel = _err(y, ref)
+            assert rel < 1e-2 and torch.isfinite(y.float()).all(), (var, mx, rel)
+    finally:
+        L.check(fluxlib.fluxb200_set_flag(b"attn_variant", 0))
+
+
 @pytest.mark.parametrize("boost", [4.0, 60.0])
 def test_sdpa_late_large_scores(fluxlib, boost):
     """Keys of the later kv blocks are much larger than the early ones, so the running max jumps after the first
