@@ -283,3 +283,26 @@ def test_two_devices_driven_from_two_threads(fluxlib):
     for dev in (0, 1):
         assert torch.equal(solo[dev], both[dev])
     assert torch.equal(solo[0], solo[1])
+
+
+def test_reference_arm_line_has_the_contract_keys():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to ours): one JSON line, exactly K timed samples,
+    the same metric / unit / config builder as our arm, `cpu_baseline` and a zero-copy `e2e` object."""
+    import json
+    import subprocess
+    import sys
+    sys.path.insert(0, str(ROOT))
+    import bench
+    out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                          "--height", "256", "--width", "256", "--num-steps", "4"],
+                         capture_output=True, text=True, timeout=600, check=True).stdout.strip().splitlines()[-1]
+    j = json.loads(out)
+    assert j["impl"] == "reference" and j["metric"] == bench.METRIC and j["unit"] == bench.UNIT
+    assert j["steps"] == 1 and j["higher_is_better"] is True and j["value"] > 0 and j["ms_per_step"] > 0
+    ours = bench.workload_config(256, 256, 4, 1, 1, None)
+    assert {k: j["config"][k] for k in ours} == ours  # same config object as our arm, plus the reference-arm notes
+    cb = j["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == j["value"] and "sample" in cb
+    assert j["e2e"] == {"value": j["value"], "unit": bench.UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # the reported per-step time is the measured sample, not an extrapolated image (it must fit the driver's clock)
+    assert j["ms_per_step"] / 1e3 < j["wall_s"]
