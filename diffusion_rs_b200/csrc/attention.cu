@@ -584,6 +584,9 @@ static const AttnVariant kAttnVariants[] = {
     FB_ATTN_VARIANT(false, 0x88, 1, false, 1, "1 CTA, poly 1/4, no MUFU ping-pong"),
     FB_ATTN_VARIANT(false, 0x08, 1, true, 1, "1 CTA, poly 1/8, ping-pong"),
     FB_ATTN_VARIANT(false, 0x08, 1, false, 1, "1 CTA, poly 1/8, no MUFU ping-pong"),
+    FB_ATTN_VARIANT(false, 0x88, 4, false, 1, "1 CTA, poly 1/4, P in 4 instalments, no MUFU ping-pong"),
+    FB_ATTN_VARIANT(false, 0x88, 2, true, 1, "1 CTA, poly 1/4, P in 2 instalments"),
+    FB_ATTN_VARIANT(false, 0x88, 2, false, 1, "1 CTA, poly 1/4, P in 2 instalments, no MUFU ping-pong"),
 };
 static constexpr int kNumAttnVariants = sizeof(kAttnVariants) / sizeof(kAttnVariants[0]);
 
